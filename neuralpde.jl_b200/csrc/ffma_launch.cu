@@ -1,0 +1,104 @@
+// ffma_launch.cu -- gradient/loss reduction kernels and the host-callable launchers of the
+// FFMA path.
+#include <cuda_runtime.h>
+#include "dev_types.h"
+
+namespace pinn {
+
+// ------------------------------------------------------------------------------------------
+// Fixed-order reduction of the per-CTA partials; also turns the per-term sums into losses.
+//   out_grad[i]      = sum_b partial[b][i]
+//   out_terms[k]     = scale_k * sum_b term_sums[b][k]          (unweighted L_k)
+//   out_total        = sum_k w_k * out_terms[k]
+// When `packed` is non-null (multi-GPU), grad and the term losses are written contiguously
+// into packed[0..n_theta+n_terms) for a single allreduce and finish_kernel unpacks.
+template <typename real>
+__global__ void reduce_kernel(const real* __restrict__ partial, const double* __restrict__ term_sums, int nb,
+                              long long n_theta, int n_terms, const ScaleW sw,
+                              real* out_grad, real* out_terms, real* out_total, int want_grad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (want_grad && i < n_theta) {
+    real s = real(0);
+    for (int b = 0; b < nb; ++b) s += partial[(long long)b * n_theta + i];
+    out_grad[i] = s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < 32) {
+    double tot = 0.0;
+    for (int k = 0; k < n_terms; ++k) {
+      double s = 0.0;
+      for (int b = threadIdx.x; b < nb; b += 32) s += term_sums[(long long)b * PINN_MAX_TERMS + k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      double Lk = s * sw.scale[k];
+      tot += Lk * sw.w[k];
+      if (threadIdx.x == 0) out_terms[k] = real(Lk);
+    }
+    if (threadIdx.x == 0 && out_total) *out_total = real(tot);
+  }
+}
+
+// after the allreduce of packed = [grad | term losses]: total = sum_k w_k L_k
+template <typename real>
+__global__ void finish_kernel(const real* __restrict__ packed_terms, int n_terms, const ScaleW sw,
+                              real* out_terms, real* out_total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double tot = 0.0;
+    for (int k = 0; k < n_terms; ++k) {
+      double Lk = (double)packed_terms[k];
+      out_terms[k] = real(Lk);
+      tot += Lk * sw.w[k];
+    }
+    *out_total = real(tot);
+  }
+}
+
+// ---- host-callable launchers -------------------------------------------------------------------
+size_t ffma_smem_bytes(int dtype, long long buf_elems, int w_area, bool bufs_smem) {
+  size_t es = dtype == PINN_F64 ? 8 : 4;
+  size_t n = (bufs_smem ? 2 * (size_t)buf_elems : 0) + (size_t)w_area + PINN_MAX_DIM * kTilePts +
+             2 * PINN_MAX_TAPS * kTilePts + 2 * kTilePts;
+  size_t bytes = n * es;
+  bytes = (bytes + 7) & ~size_t(7);
+  bytes += PINN_MAX_TERMS * sizeof(double);
+  return bytes;
+}
+
+cudaError_t ffma_launch_float_smem(const FfmaArgs& a, int grid, size_t smem, cudaStream_t st);
+cudaError_t ffma_launch_float_gmem(const FfmaArgs& a, int grid, size_t smem, cudaStream_t st);
+cudaError_t ffma_launch_double_smem(const FfmaArgs& a, int grid, size_t smem, cudaStream_t st);
+cudaError_t ffma_launch_double_gmem(const FfmaArgs& a, int grid, size_t smem, cudaStream_t st);
+
+cudaError_t ffma_launch(int dtype, bool bufs_smem, const FfmaArgs& a, int grid, size_t smem, cudaStream_t st) {
+  if (dtype == PINN_F64)
+    return bufs_smem ? ffma_launch_double_smem(a, grid, smem, st) : ffma_launch_double_gmem(a, grid, smem, st);
+  return bufs_smem ? ffma_launch_float_smem(a, grid, smem, st) : ffma_launch_float_gmem(a, grid, smem, st);
+}
+
+cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+                          int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
+                          int want_grad, cudaStream_t st) {
+  long long n = want_grad ? n_theta : 1;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks < 1) blocks = 1;
+  if (dtype == PINN_F64)
+    reduce_kernel<double><<<blocks, 256, 0, st>>>((const double*)partial, term_sums, nb, n_theta, n_terms, scale_w,
+                                                   (double*)out_grad, (double*)out_terms, (double*)out_total,
+                                                   want_grad);
+  else
+    reduce_kernel<float><<<blocks, 256, 0, st>>>((const float*)partial, term_sums, nb, n_theta, n_terms, scale_w,
+                                                  (float*)out_grad, (float*)out_terms, (float*)out_total, want_grad);
+  return cudaGetLastError();
+}
+
+cudaError_t finish_launch(int dtype, const void* packed_terms, int n_terms, const ScaleW& scale_w, void* out_terms,
+                          void* out_total, cudaStream_t st) {
+  if (dtype == PINN_F64)
+    finish_kernel<double><<<1, 32, 0, st>>>((const double*)packed_terms, n_terms, scale_w, (double*)out_terms,
+                                             (double*)out_total);
+  else
+    finish_kernel<float><<<1, 32, 0, st>>>((const float*)packed_terms, n_terms, scale_w, (float*)out_terms,
+                                            (float*)out_total);
+  return cudaGetLastError();
+}
+
+}  // namespace pinn

@@ -1,0 +1,686 @@
+// pinn_abi.cu -- host side of the C ABI declared in include/pinn_b200.h: descriptor
+// validation and lowering to the device representation, workspace ownership, kernel
+// launch sequencing, host-buffer staging and the optional NCCL gradient allreduce.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "dev_types.h"
+
+namespace pinn {
+size_t ffma_smem_bytes(int dtype, long long buf_elems, int w_area, bool bufs_smem);
+cudaError_t ffma_launch(int dtype, bool bufs_smem, const FfmaArgs& a, int grid, size_t smem, cudaStream_t st);
+cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+                          int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
+                          int want_grad, cudaStream_t st);
+cudaError_t finish_launch(int dtype, const void* packed_terms, int n_terms, const ScaleW& scale_w, void* out_terms,
+                          void* out_total, cudaStream_t st);
+}  // namespace pinn
+
+using namespace pinn;
+
+// ---- minimal NCCL binding (resolved at run time so single-GPU use has no dependency) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclFloat32 = 7, ncclFloat64 = 8, ncclSumOp = 0 };
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+
+static thread_local std::string g_err;
+static int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CUDA_TRY(expr)                                                                  \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) return fail("%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+static bool load_nccl() {
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    g_nccl.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return false;
+  g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
+  return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce;
+}
+
+struct pinn_engine {
+  int dtype = 0, mode = 0, device = 0;
+  size_t es = 4;
+  DevProblem* hprob = nullptr;   // host copy (heap: ~250 KB)
+  DevProblem* dprob = nullptr;   // device copy
+  int n_terms = 0;
+  long long n_theta = 0;
+  double term_scale[PINN_MAX_TERMS];     // WSUM scale (MEAN: 1/n_global at launch time)
+  int reduction[PINN_MAX_TERMS];
+  long long n_global[PINN_MAX_TERMS];
+  bool n_global_set[PINN_MAX_TERMS];
+  double flops_per_point[PINN_MAX_TERMS];
+  TermDyn dyn[PINN_MAX_TERMS];
+  int total_tiles = 0;
+  // launch geometry
+  int num_sms = 0;
+  size_t smem = 0;
+  bool bufs_smem = true;
+  int weights_resident = 0;
+  int w_area = 0, ldc = 0;
+  long long buf_elems = 0, stash_per_cta = 0;
+  // workspaces (device)
+  void* partial = nullptr;
+  double* term_sums = nullptr;
+  void* stash = nullptr;
+  void* gbufs = nullptr;
+  void* packed = nullptr;        // [n_theta + n_terms] allreduce buffer
+  long long ws_bytes = 0;
+  // engine-owned point copies
+  void* own_pts[PINN_MAX_TERMS];
+  size_t own_pts_cap[PINN_MAX_TERMS];
+  void* own_qw[PINN_MAX_TERMS];
+  size_t own_qw_cap[PINN_MAX_TERMS];
+  // host staging for the *_host entry points
+  void* d_theta = nullptr;
+  void* d_grad = nullptr;
+  void* d_out = nullptr;         // [n_terms + 1] term losses then total
+  void* h_pin_in = nullptr;      // pinned theta
+  void* h_pin_out = nullptr;     // pinned grad + losses
+  cudaStream_t own_stream = nullptr;
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1;
+  // introspection
+  long long launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+};
+
+static int dev_alloc(void** p, size_t bytes, pinn_engine* e) {
+  if (bytes == 0) bytes = 16;
+  cudaError_t err = cudaMalloc(p, bytes);
+  if (err != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(err));
+  e->ws_bytes += (long long)bytes;
+  return 0;
+}
+
+static void retile(pinn_engine* e) {
+  int t0 = 0;
+  for (int t = 0; t < e->n_terms; ++t) {
+    e->dyn[t].tile0 = t0;
+    e->dyn[t].n_tiles = (int)((e->dyn[t].n + kTilePts - 1) / kTilePts);
+    t0 += e->dyn[t].n_tiles;
+  }
+  e->total_tiles = t0;
+}
+
+// ---- descriptor validation + lowering -----------------------------------------------------------
+static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
+  if (!d) return fail("pinn_create: null descriptor");
+  if (d->abi_version != PINN_ABI_VERSION)
+    return fail("pinn_create: descriptor abi_version %d, library %d", d->abi_version, PINN_ABI_VERSION);
+  if (d->dtype != PINN_F32 && d->dtype != PINN_F64) return fail("pinn_create: unknown dtype %d", d->dtype);
+  if (d->mode < PINN_MODE_FFMA || d->mode > PINN_MODE_TC_SPLIT) return fail("pinn_create: unknown mode %d", d->mode);
+  if (d->mode != PINN_MODE_FFMA)
+    return fail("pinn_create: mode %d (tcgen05) is not available in this build for this problem", d->mode);
+  if (d->n_nets < 1 || d->n_nets > PINN_MAX_NETS) return fail("pinn_create: n_nets=%d out of range [1,%d]", d->n_nets, PINN_MAX_NETS);
+  if (d->n_terms < 1 || d->n_terms > PINN_MAX_TERMS)
+    return fail("pinn_create: n_terms=%d out of range [1,%d]", d->n_terms, PINN_MAX_TERMS);
+  if (d->n_params < 0 || d->n_params > PINN_MAX_PARAMS)
+    return fail("pinn_create: n_params=%d out of range [0,%d]", d->n_params, PINN_MAX_PARAMS);
+  if (!d->nets || !d->terms) return fail("pinn_create: null nets/terms");
+  if (d->n_theta <= 0) return fail("pinn_create: n_theta must be positive");
+
+  DevProblem& P = *e->hprob;
+  memset(&P, 0, sizeof(DevProblem));
+  P.n_nets = d->n_nets; P.n_terms = d->n_terms; P.n_params = d->n_params;
+  P.param_off = d->param_offset; P.n_theta = d->n_theta;
+  if (d->n_params > 0 && (d->param_offset < 0 || d->param_offset + d->n_params > d->n_theta))
+    return fail("pinn_create: theta.p block [%lld,+%d) outside theta (n_theta=%lld)", (long long)d->param_offset,
+                d->n_params, (long long)d->n_theta);
+
+  int max_w8 = 8;
+  long long resident = 0;
+  for (int k = 0; k < d->n_nets; ++k) {
+    const pinn_net_desc& nd = d->nets[k];
+    DevNet& n = P.nets[k];
+    if (nd.n_layers < 1 || nd.n_layers > PINN_MAX_LAYERS)
+      return fail("pinn_create: net %d has %d layers (supported 1..%d)", k, nd.n_layers, PINN_MAX_LAYERS);
+    if (!nd.dims || !nd.acts) return fail("pinn_create: net %d null dims/acts", k);
+    n.n_layers = nd.n_layers;
+    long long off = nd.theta_offset;
+    if (off < 0) return fail("pinn_create: net %d negative theta_offset", k);
+    for (int l = 0; l <= nd.n_layers; ++l) {
+      if (nd.dims[l] < 1) return fail("pinn_create: net %d dims[%d]=%d must be >= 1", k, l, nd.dims[l]);
+      n.dims[l] = nd.dims[l];
+      max_w8 = std::max(max_w8, (nd.dims[l] + 7) & ~7);
+    }
+    if (n.dims[0] > PINN_MAX_IN) return fail("pinn_create: net %d input dimension %d > %d", k, n.dims[0], PINN_MAX_IN);
+    for (int l = 0; l < nd.n_layers; ++l) {
+      if (nd.acts[l] < PINN_ACT_IDENTITY || nd.acts[l] > PINN_ACT_SWISH)
+        return fail("pinn_create: net %d layer %d unknown activation %d", k, l, nd.acts[l]);
+      n.acts[l] = nd.acts[l];
+      n.w_off[l] = off; off += (long long)n.dims[l] * n.dims[l + 1];
+      n.b_off[l] = off; off += n.dims[l + 1];
+      int in8 = (n.dims[l] + 7) & ~7, out8 = (n.dims[l + 1] + 7) & ~7;
+      n.ws_off[l] = (int)resident; resident += (long long)in8 * out8;
+      n.bs_off[l] = (int)resident; resident += out8;
+    }
+    if (off > d->n_theta)
+      return fail("pinn_create: net %d parameters [%lld,%lld) exceed n_theta=%lld", k, (long long)nd.theta_offset, off,
+                  (long long)d->n_theta);
+    n.max_width8 = max_w8;
+  }
+
+  int maxC = 1;
+  long long stash_max = 0;
+  for (int t = 0; t < d->n_terms; ++t) {
+    const pinn_term_desc& td = d->terms[t];
+    DevTerm& T = P.terms[t];
+    if (td.dim < 1 || td.dim > PINN_MAX_DIM) return fail("pinn_create: term %d dim=%d out of range [1,%d]", t, td.dim, PINN_MAX_DIM);
+    if (td.n_taps < 1)
+      return fail("pinn_create: term %d has no network taps (an equation such as 0 ~ 0 cannot be trained on)", t);
+    if (td.n_taps > PINN_MAX_TAPS) return fail("pinn_create: term %d has %d taps (max %d)", t, td.n_taps, PINN_MAX_TAPS);
+    if (td.n_instr < 1 || td.n_instr > PINN_MAX_INSTR)
+      return fail("pinn_create: term %d program length %d out of range [1,%d]", t, td.n_instr, PINN_MAX_INSTR);
+    if (!td.taps || !td.prog || !td.net_rows) return fail("pinn_create: term %d null taps/prog/net_rows", t);
+    if (td.reduction != PINN_REDUCE_MEAN && td.reduction != PINN_REDUCE_WSUM)
+      return fail("pinn_create: term %d unknown reduction %d", t, td.reduction);
+    T.dim = td.dim; T.n_taps = td.n_taps; T.n_instr = td.n_instr;
+    T.weighted = td.reduction == PINN_REDUCE_WSUM;
+    e->reduction[t] = td.reduction;
+    e->term_scale[t] = td.reduction == PINN_REDUCE_WSUM ? td.scale : 1.0;
+
+    // slots: networks in order of first use
+    int slot_of[PINN_MAX_NETS];
+    for (int k = 0; k < PINN_MAX_NETS; ++k) slot_of[k] = -1;
+    T.n_used = 0;
+    for (int i = 0; i < td.n_taps; ++i) {
+      const pinn_tap_desc& tp = td.taps[i];
+      if (tp.net < 0 || tp.net >= d->n_nets) return fail("pinn_create: term %d tap %d names network %d", t, i, tp.net);
+      if (slot_of[tp.net] < 0) {
+        slot_of[tp.net] = T.n_used;
+        T.used_net[T.n_used] = tp.net;
+        DevChan& ch = T.chan[T.n_used];
+        ch.C = 1; ch.n1 = 0; ch.n2 = 0;
+        const int din = P.nets[tp.net].dims[0];
+        for (int j = 0; j < din; ++j) {
+          int r = td.net_rows[tp.net * PINN_MAX_IN + j];
+          if (r < 0 || r >= td.dim)
+            return fail("pinn_create: term %d network %d input %d maps to point row %d (dim=%d)", t, tp.net, j, r, td.dim);
+          ch.rows[j] = r;
+        }
+        ++T.n_used;
+      }
+    }
+    // channels
+    for (int pass = 1; pass <= 2; ++pass) {
+      for (int i = 0; i < td.n_taps; ++i) {
+        const pinn_tap_desc& tp = td.taps[i];
+        const int din = P.nets[tp.net].dims[0];
+        DevChan& ch = T.chan[slot_of[tp.net]];
+        if (tp.order < 0 || tp.order > 2)
+          return fail("pinn_create: term %d tap %d has derivative order %d; orders 0..2 are supported", t, i, tp.order);
+        if (tp.out < 0 || tp.out >= P.nets[tp.net].dims[P.nets[tp.net].n_layers])
+          return fail("pinn_create: term %d tap %d output component %d out of range", t, i, tp.out);
+        for (int q = 0; q < tp.order; ++q)
+          if (tp.dir[q] < 0 || tp.dir[q] >= din)
+            return fail("pinn_create: term %d tap %d direction %d out of range for a %d-input network", t, i, tp.dir[q], din);
+        if (pass == 1) {
+          // first-derivative channels needed directly or as intermediates of second derivatives
+          for (int q = 0; q < tp.order; ++q) {
+            int found = -1;
+            for (int j = 0; j < ch.n1; ++j) if (ch.dir1[j] == tp.dir[q]) found = j;
+            if (found < 0) ch.dir1[ch.n1++] = tp.dir[q];
+          }
+        } else if (tp.order == 2) {
+          int a = -1, b = -1;
+          for (int j = 0; j < ch.n1; ++j) { if (ch.dir1[j] == tp.dir[0]) a = j; if (ch.dir1[j] == tp.dir[1]) b = j; }
+          if (a > b) std::swap(a, b);
+          int found = -1;
+          for (int s = 0; s < ch.n2; ++s) if (ch.s_a[s] == a && ch.s_b[s] == b) found = s;
+          if (found < 0) {
+            if (1 + ch.n1 + ch.n2 >= PINN_MAX_CH)
+              return fail("pinn_create: term %d network %d needs more than %d channels", t, tp.net, PINN_MAX_CH);
+            ch.s_a[ch.n2] = a; ch.s_b[ch.n2] = b; ++ch.n2;
+          }
+        }
+      }
+    }
+    long long stash = 0;
+    for (int s = 0; s < T.n_used; ++s) {
+      DevChan& ch = T.chan[s];
+      ch.C = 1 + ch.n1 + ch.n2;
+      if (ch.C > PINN_MAX_CH) return fail("pinn_create: term %d needs %d channels (max %d)", t, ch.C, PINN_MAX_CH);
+      maxC = std::max(maxC, ch.C);
+      const DevNet& n = P.nets[T.used_net[s]];
+      for (int l = 0; l < n.n_layers; ++l) {
+        ch.stash_off[l] = (int)stash;
+        stash += (long long)ch.C * n.dims[l + 1] * kTilePts;
+      }
+    }
+    stash_max = std::max(stash_max, stash);
+    // tap -> (slot, channel)
+    for (int i = 0; i < td.n_taps; ++i) {
+      const pinn_tap_desc& tp = td.taps[i];
+      const DevChan& ch = T.chan[slot_of[tp.net]];
+      T.tap_slot[i] = slot_of[tp.net];
+      T.tap_out[i] = tp.out;
+      if (tp.order == 0) T.tap_ch[i] = 0;
+      else if (tp.order == 1) {
+        int j = 0; while (ch.dir1[j] != tp.dir[0]) ++j;
+        T.tap_ch[i] = 1 + j;
+      } else {
+        int a = -1, b = -1;
+        for (int j = 0; j < ch.n1; ++j) { if (ch.dir1[j] == tp.dir[0]) a = j; if (ch.dir1[j] == tp.dir[1]) b = j; }
+        if (a > b) std::swap(a, b);
+        int s = 0; while (!(ch.s_a[s] == a && ch.s_b[s] == b)) ++s;
+        T.tap_ch[i] = 1 + ch.n1 + s;
+      }
+    }
+    // program
+    bool any_tap = false;
+    for (int i = 0; i < td.n_instr; ++i) {
+      const pinn_instr& in = td.prog[i];
+      DevInstr& o = T.prog[i];
+      o.op = in.op; o.a = in.a; o.b = in.b; o.pad = 0; o.imm = in.imm;
+      auto val_ok = [&](int v) { return v >= 0 && v < i; };
+      switch (in.op) {
+        case PINN_OP_CONST: break;
+        case PINN_OP_COORD:
+          if (in.a < 0 || in.a >= td.dim) return fail("pinn_create: term %d instr %d COORD row %d out of range", t, i, in.a);
+          break;
+        case PINN_OP_TAP:
+          if (in.a < 0 || in.a >= td.n_taps) return fail("pinn_create: term %d instr %d TAP %d out of range", t, i, in.a);
+          any_tap = true;
+          break;
+        case PINN_OP_PARAM:
+          if (in.a < 0 || in.a >= d->n_params) return fail("pinn_create: term %d instr %d PARAM %d out of range", t, i, in.a);
+          break;
+        case PINN_OP_ADD: case PINN_OP_SUB: case PINN_OP_MUL: case PINN_OP_DIV: case PINN_OP_POW:
+          if (!val_ok(in.a) || !val_ok(in.b)) return fail("pinn_create: term %d instr %d operand out of range", t, i);
+          break;
+        case PINN_OP_NEG: case PINN_OP_POWI: case PINN_OP_SIN: case PINN_OP_COS: case PINN_OP_EXP:
+        case PINN_OP_LOG: case PINN_OP_TANH: case PINN_OP_SQRT: case PINN_OP_ABS:
+          if (!val_ok(in.a)) return fail("pinn_create: term %d instr %d operand out of range", t, i);
+          break;
+        default:
+          return fail("pinn_create: term %d instr %d unknown opcode %d", t, i, in.op);
+      }
+    }
+    if (!any_tap)
+      return fail("pinn_create: term %d residual program never reads a tap (nothing depends on theta)", t);
+    // algorithmic flops per point: 6 * sum_nets C * S
+    double f = 0;
+    for (int s = 0; s < T.n_used; ++s) {
+      const DevNet& n = P.nets[T.used_net[s]];
+      double S = 0;
+      for (int l = 0; l < n.n_layers; ++l) S += (double)n.dims[l] * n.dims[l + 1];
+      f += 6.0 * T.chan[s].C * S;
+    }
+    e->flops_per_point[t] = f;
+  }
+
+  // ---- launch geometry -------------------------------------------------------------------------
+  const int TP = kTilePts + (int)(16 / e->es);
+  e->ldc = max_w8 * TP;
+  e->buf_elems = (long long)maxC * e->ldc;
+  e->stash_per_cta = (stash_max + 3) & ~3LL;
+  const long long panel = (long long)(kWarps * 8) * max_w8 + kWarps * 8;   // 64 x max_width8 (+ bias)
+  int max_smem = 0;
+  cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, e->device);
+  if (max_smem <= 0) max_smem = 227 * 1024;
+  struct Opt { bool bufs; bool res; };
+  const Opt opts[3] = {{true, true}, {true, false}, {false, false}};
+  bool chosen = false;
+  for (const Opt& o : opts) {
+    long long wa = o.res ? resident : panel;
+    wa = (wa + 3) & ~3LL;
+    if (wa > (1LL << 30)) continue;
+    size_t need = ffma_smem_bytes(e->dtype, e->buf_elems, (int)wa, o.bufs);
+    if (need <= (size_t)max_smem) {
+      e->bufs_smem = o.bufs; e->weights_resident = o.res ? 1 : 0; e->w_area = (int)wa; e->smem = need;
+      chosen = true;
+      break;
+    }
+  }
+  if (!chosen)
+    return fail("pinn_create: a %d-wide layer panel does not fit in shared memory (%d bytes)", max_w8, max_smem);
+  return 0;
+}
+
+extern "C" {
+
+const char* pinn_last_error(void) { return g_err.c_str(); }
+int pinn_abi_version(void) { return PINN_ABI_VERSION; }
+
+int pinn_destroy(pinn_handle e) {
+  if (!e) return 0;
+  cudaSetDevice(e->device);
+  if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
+  void* ptrs[] = {e->dprob, e->partial, e->term_sums, e->stash, e->gbufs, e->packed,
+                  e->d_theta, e->d_grad, e->d_out};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (int t = 0; t < PINN_MAX_TERMS; ++t) {
+    if (e->own_pts[t]) cudaFree(e->own_pts[t]);
+    if (e->own_qw[t]) cudaFree(e->own_qw[t]);
+  }
+  if (e->h_pin_in) cudaFreeHost(e->h_pin_in);
+  if (e->h_pin_out) cudaFreeHost(e->h_pin_out);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  delete e->hprob;
+  delete e;
+  return 0;
+}
+
+int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
+  if (!out) return fail("pinn_create: null output handle");
+  *out = nullptr;
+  if (!d) return fail("pinn_create: null descriptor");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail("pinn_create: no CUDA device available (%s); this engine has no CPU fallback",
+                cudaGetErrorString(ce));
+  if (d->device < 0 || d->device >= ndev) return fail("pinn_create: device %d not in [0,%d)", d->device, ndev);
+  CUDA_TRY(cudaSetDevice(d->device));
+  pinn_engine* e = new pinn_engine();
+  memset(e->own_pts, 0, sizeof e->own_pts); memset(e->own_qw, 0, sizeof e->own_qw);
+  memset(e->own_pts_cap, 0, sizeof e->own_pts_cap); memset(e->own_qw_cap, 0, sizeof e->own_qw_cap);
+  memset(e->dyn, 0, sizeof e->dyn); memset(e->n_global_set, 0, sizeof e->n_global_set);
+  memset(e->n_global, 0, sizeof e->n_global);
+  e->hprob = new DevProblem();
+  e->dtype = d->dtype; e->mode = d->mode; e->device = d->device;
+  e->es = d->dtype == PINN_F64 ? 8 : 4;
+  e->n_terms = d->n_terms; e->n_theta = d->n_theta;
+  if (lower_problem(d, e)) { pinn_destroy(e); return 1; }
+  cudaDeviceGetAttribute(&e->num_sms, cudaDevAttrMultiProcessorCount, e->device);
+  if (e->num_sms <= 0) e->num_sms = 148;
+
+#define TRY_OR_DESTROY(x) do { if (x) { pinn_destroy(e); return 1; } } while (0)
+  TRY_OR_DESTROY(dev_alloc((void**)&e->dprob, sizeof(DevProblem), e));
+  cudaError_t err = cudaMemcpy(e->dprob, e->hprob, sizeof(DevProblem), cudaMemcpyHostToDevice);
+  if (err != cudaSuccess) { fail("pinn_create: upload failed: %s", cudaGetErrorString(err)); pinn_destroy(e); return 1; }
+  const size_t g = (size_t)e->num_sms;
+  TRY_OR_DESTROY(dev_alloc(&e->partial, g * (size_t)e->n_theta * e->es, e));
+  TRY_OR_DESTROY(dev_alloc((void**)&e->term_sums, g * PINN_MAX_TERMS * sizeof(double), e));
+  TRY_OR_DESTROY(dev_alloc(&e->stash, g * (size_t)e->stash_per_cta * e->es, e));
+  if (!e->bufs_smem) TRY_OR_DESTROY(dev_alloc(&e->gbufs, g * 2 * (size_t)e->buf_elems * e->es, e));
+  TRY_OR_DESTROY(dev_alloc(&e->packed, ((size_t)e->n_theta + PINN_MAX_TERMS) * e->es, e));
+  TRY_OR_DESTROY(dev_alloc(&e->d_theta, (size_t)e->n_theta * e->es, e));
+  TRY_OR_DESTROY(dev_alloc(&e->d_grad, (size_t)e->n_theta * e->es, e));
+  TRY_OR_DESTROY(dev_alloc(&e->d_out, (PINN_MAX_TERMS + 1) * e->es, e));
+  err = cudaMallocHost(&e->h_pin_in, (size_t)e->n_theta * e->es);
+  if (err == cudaSuccess) err = cudaMallocHost(&e->h_pin_out, ((size_t)e->n_theta + PINN_MAX_TERMS + 1) * e->es);
+  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+  if (err == cudaSuccess) err = cudaEventCreate(&e->ev0);
+  if (err == cudaSuccess) err = cudaEventCreate(&e->ev1);
+  if (err != cudaSuccess) { fail("pinn_create: host staging setup failed: %s", cudaGetErrorString(err)); pinn_destroy(e); return 1; }
+#undef TRY_OR_DESTROY
+  retile(e);
+  *out = e;
+  return 0;
+}
+
+static int check_term(pinn_handle e, int32_t term, const char* fn) {
+  if (!e) return fail("%s: null handle", fn);
+  if (term < 0 || term >= e->n_terms) return fail("%s: term %d out of range [0,%d)", fn, term, e->n_terms);
+  return 0;
+}
+
+int pinn_set_points(pinn_handle e, int32_t term, const void* dev_pts, int64_t n, const void* dev_w) {
+  if (check_term(e, term, "pinn_set_points")) return 1;
+  if (n < 0) return fail("pinn_set_points: negative point count");
+  if (n > 0 && !dev_pts) return fail("pinn_set_points: null points");
+  if (e->reduction[term] == PINN_REDUCE_WSUM && n > 0 && !dev_w)
+    return fail("pinn_set_points: term %d is a weighted-sum (quadrature) term and needs weights", term);
+  if (n > (int64_t)kTilePts * 60000000LL) return fail("pinn_set_points: too many points");
+  e->dyn[term].pts = dev_pts; e->dyn[term].qw = dev_w; e->dyn[term].n = n;
+  retile(e);
+  return 0;
+}
+
+static int grow(void** p, size_t* cap, size_t need, pinn_engine* e) {
+  if (need <= *cap) return 0;
+  if (*p) { cudaFree(*p); e->ws_bytes -= (long long)*cap; *p = nullptr; *cap = 0; }
+  size_t want = need + need / 8;
+  if (dev_alloc(p, want, e)) return 1;
+  *cap = want;
+  return 0;
+}
+
+int pinn_set_points_host(pinn_handle e, int32_t term, const void* host_pts, int64_t n, const void* host_w,
+                         void* stream) {
+  if (check_term(e, term, "pinn_set_points_host")) return 1;
+  if (n < 0) return fail("pinn_set_points_host: negative point count");
+  if (n > 0 && !host_pts) return fail("pinn_set_points_host: null points");
+  if (e->reduction[term] == PINN_REDUCE_WSUM && n > 0 && !host_w)
+    return fail("pinn_set_points_host: term %d is a weighted-sum (quadrature) term and needs weights", term);
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int dim = e->hprob->terms[term].dim;
+  cudaStream_t st = (cudaStream_t)stream;
+  size_t bytes = (size_t)n * dim * e->es;
+  if (grow(&e->own_pts[term], &e->own_pts_cap[term], bytes, e)) return 1;
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(e->own_pts[term], host_pts, bytes, cudaMemcpyHostToDevice, st));
+  const void* w = nullptr;
+  if (host_w) {
+    size_t wb = (size_t)n * e->es;
+    if (grow(&e->own_qw[term], &e->own_qw_cap[term], wb, e)) return 1;
+    if (wb) CUDA_TRY(cudaMemcpyAsync(e->own_qw[term], host_w, wb, cudaMemcpyHostToDevice, st));
+    w = e->own_qw[term];
+  }
+  e->dyn[term].pts = e->own_pts[term]; e->dyn[term].qw = w; e->dyn[term].n = n;
+  retile(e);
+  return 0;
+}
+
+int pinn_set_global_count(pinn_handle e, int32_t term, int64_t n_global) {
+  if (check_term(e, term, "pinn_set_global_count")) return 1;
+  if (n_global <= 0) return fail("pinn_set_global_count: n_global must be positive");
+  e->n_global[term] = n_global; e->n_global_set[term] = true;
+  return 0;
+}
+
+// scale_k (so that L_k = scale_k * sum_p qw r^2) and the loss weights w_k
+static int prepare_scales(pinn_engine* e, const double* host_weights, FfmaArgs& a, ScaleW& sw) {
+  for (int t = 0; t < e->n_terms; ++t) {
+    double sc;
+    if (e->reduction[t] == PINN_REDUCE_MEAN) {
+      long long ng = e->n_global_set[t] ? e->n_global[t] : e->dyn[t].n;
+      if (ng <= 0) return fail("pinn_loss_grad: term %d has no points (pinn_set_points was not called or n == 0)", t);
+      sc = 1.0 / (double)ng;
+    } else {
+      sc = e->term_scale[t];
+    }
+    double w = host_weights ? host_weights[t] : 1.0;
+    sw.scale[t] = sc;
+    sw.w[t] = w;
+    a.seed[t] = sc * w;
+  }
+  return 0;
+}
+
+static void fill_args(pinn_engine* e, FfmaArgs& a, const void* theta, int mode) {
+  a.prob = e->dprob; a.theta = theta; a.partial = e->partial; a.term_sums = e->term_sums; a.stash = e->stash;
+  a.gbufs = e->gbufs; a.stash_per_cta = e->stash_per_cta; a.buf_elems = e->buf_elems; a.ldc = e->ldc;
+  a.w_area = e->w_area; a.weights_resident = e->weights_resident; a.n_tiles = e->total_tiles;
+  a.tile_begin = 0; a.tile_end = e->total_tiles; a.mode = mode; a.resid_out = nullptr;
+  for (int t = 0; t < PINN_MAX_TERMS; ++t) a.dyn[t] = e->dyn[t];
+}
+
+int pinn_loss_grad(pinn_handle e, const void* dev_theta, const double* host_weights, void* dev_grad,
+                   void* dev_term_losses, void* dev_total, void* stream) {
+  if (!e) return fail("pinn_loss_grad: null handle");
+  if (!dev_theta || !dev_term_losses || !dev_total) return fail("pinn_loss_grad: null theta/term_losses/total");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int t = 0; t < e->n_terms; ++t)
+    if (e->dyn[t].n <= 0 && !(e->nranks > 1 && e->n_global_set[t]))
+      return fail("pinn_loss_grad: term %d has no points (call pinn_set_points first)", t);
+  if (e->total_tiles <= 0) return fail("pinn_loss_grad: no collocation points on this rank");
+  FfmaArgs a;
+  memset(&a, 0, sizeof a);
+  fill_args(e, a, dev_theta, dev_grad ? 0 : 1);
+  ScaleW sw;
+  memset(&sw, 0, sizeof sw);
+  if (prepare_scales(e, host_weights, a, sw)) return 1;
+  const int grid = std::min(e->num_sms, e->total_tiles);
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, st));
+  CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, st));
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
+  e->launches += 1;
+  if (e->nranks > 1) {
+    char* pk = (char*)e->packed;
+    void* pk_terms = pk + (size_t)e->n_theta * e->es;
+    CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw,
+                           e->packed, pk_terms, nullptr, dev_grad ? 1 : 0, st));
+    e->launches += 1;
+    size_t count = (size_t)e->n_terms + (dev_grad ? (size_t)e->n_theta : 0);
+    void* base = dev_grad ? e->packed : pk_terms;
+    ncclResult_t r = g_nccl.AllReduce(base, base, count, e->dtype == PINN_F64 ? ncclFloat64 : ncclFloat32, ncclSumOp,
+                                      e->comm, st);
+    if (r != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    e->launches += 1;
+    if (dev_grad) CUDA_TRY(cudaMemcpyAsync(dev_grad, e->packed, (size_t)e->n_theta * e->es, cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(finish_launch(e->dtype, pk_terms, e->n_terms, sw, dev_term_losses, dev_total, st));
+    e->launches += 1;
+  } else {
+    CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, dev_grad,
+                           dev_term_losses, dev_total, dev_grad ? 1 : 0, st));
+    e->launches += 1;
+  }
+  if (e->timing) {
+    CUDA_TRY(cudaEventSynchronize(e->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  }
+  return 0;
+}
+
+int pinn_loss_grad_host(pinn_handle e, const void* host_theta, const double* host_weights, void* host_grad,
+                        void* host_term_losses, void* host_total) {
+  if (!e) return fail("pinn_loss_grad_host: null handle");
+  if (!host_theta || !host_total) return fail("pinn_loss_grad_host: null theta/total");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->own_stream;
+  const size_t tb = (size_t)e->n_theta * e->es;
+  memcpy(e->h_pin_in, host_theta, tb);
+  CUDA_TRY(cudaMemcpyAsync(e->d_theta, e->h_pin_in, tb, cudaMemcpyHostToDevice, st));
+  char* dout = (char*)e->d_out;
+  if (pinn_loss_grad(e, e->d_theta, host_weights, host_grad ? e->d_grad : nullptr, dout,
+                     dout + (size_t)e->n_terms * e->es, st))
+    return 1;
+  char* hout = (char*)e->h_pin_out;
+  if (host_grad) CUDA_TRY(cudaMemcpyAsync(hout, e->d_grad, tb, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(hout + tb, e->d_out, ((size_t)e->n_terms + 1) * e->es, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (host_grad) memcpy(host_grad, hout, tb);
+  if (host_term_losses) memcpy(host_term_losses, hout + tb, (size_t)e->n_terms * e->es);
+  memcpy(host_total, hout + tb + (size_t)e->n_terms * e->es, e->es);
+  return 0;
+}
+
+int pinn_term_residual(pinn_handle e, int32_t term, const void* dev_theta, void* dev_r, void* stream) {
+  if (check_term(e, term, "pinn_term_residual")) return 1;
+  if (!dev_theta || !dev_r) return fail("pinn_term_residual: null theta/output");
+  if (e->dyn[term].n <= 0) return fail("pinn_term_residual: term %d has no points", term);
+  CUDA_TRY(cudaSetDevice(e->device));
+  FfmaArgs a;
+  memset(&a, 0, sizeof a);
+  fill_args(e, a, dev_theta, 2);
+  a.tile_begin = e->dyn[term].tile0;
+  a.tile_end = e->dyn[term].tile0 + e->dyn[term].n_tiles;
+  a.resid_out = dev_r;
+  const int grid = std::min(e->num_sms, e->dyn[term].n_tiles);
+  CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, (cudaStream_t)stream));
+  e->launches += 1;
+  return 0;
+}
+
+int pinn_term_residual_host(pinn_handle e, int32_t term, const void* host_theta, void* host_r) {
+  if (check_term(e, term, "pinn_term_residual_host")) return 1;
+  if (!host_theta || !host_r) return fail("pinn_term_residual_host: null theta/output");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = e->own_stream;
+  const size_t tb = (size_t)e->n_theta * e->es;
+  CUDA_TRY(cudaMemcpyAsync(e->d_theta, host_theta, tb, cudaMemcpyHostToDevice, st));
+  void* dr = nullptr;
+  size_t rb = (size_t)e->dyn[term].n * e->es;
+  CUDA_TRY(cudaMalloc(&dr, rb ? rb : 16));
+  int rc = pinn_term_residual(e, term, e->d_theta, dr, st);
+  if (!rc) {
+    cudaError_t err = cudaMemcpyAsync(host_r, dr, rb, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) rc = fail("pinn_term_residual_host: %s", cudaGetErrorString(err));
+  }
+  cudaFree(dr);
+  return rc;
+}
+
+int pinn_comm_unique_id(void* out) {
+  if (!out) return fail("pinn_comm_unique_id: null output");
+  if (!load_nccl()) return fail("pinn_comm_unique_id: libnccl.so.2 could not be loaded: %s", dlerror());
+  ncclUniqueId id;
+  ncclResult_t r = g_nccl.GetUniqueId(&id);
+  if (r != 0) return fail("ncclGetUniqueId failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  memcpy(out, &id, sizeof id);
+  return 0;
+}
+
+int pinn_comm_init(pinn_handle e, const void* uid, int32_t rank, int32_t nranks) {
+  if (!e) return fail("pinn_comm_init: null handle");
+  if (!uid) return fail("pinn_comm_init: null unique id");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail("pinn_comm_init: bad rank %d / nranks %d", rank, nranks);
+  if (!load_nccl()) return fail("pinn_comm_init: libnccl.so.2 could not be loaded: %s", dlerror());
+  CUDA_TRY(cudaSetDevice(e->device));
+  ncclUniqueId id;
+  memcpy(&id, uid, sizeof id);
+  ncclResult_t r = g_nccl.CommInitRank(&e->comm, nranks, id, rank);
+  if (r != 0) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+  e->rank = rank; e->nranks = nranks;
+  return 0;
+}
+
+int64_t pinn_launch_count(pinn_handle e) { return e ? e->launches : 0; }
+int pinn_set_timing(pinn_handle e, int32_t enable) {
+  if (!e) return fail("pinn_set_timing: null handle");
+  e->timing = enable != 0;
+  return 0;
+}
+double pinn_last_kernel_ms(pinn_handle e) { return e ? (double)e->last_ms : 0.0; }
+int64_t pinn_workspace_bytes(pinn_handle e) { return e ? e->ws_bytes : 0; }
+double pinn_flops_per_eval(pinn_handle e) {
+  if (!e) return 0.0;
+  double f = 0;
+  for (int t = 0; t < e->n_terms; ++t) f += e->flops_per_point[t] * (double)e->dyn[t].n;
+  return f;
+}
+
+}  // extern "C"

@@ -1,0 +1,70 @@
+"""GPU parity: the CUDA path (through the C ABI) against the float64 oracle on the same
+seeded inputs.  Tolerances: fp64 engine 1e-9 (same algorithm, different summation order);
+fp32 engine loss rtol 1e-5 (BASELINE.json north_star), gradient relative L2 error 2e-4."""
+import numpy as np
+import pytest
+
+import neuralpde_jl_b200 as npde
+from neuralpde_jl_b200 import configs
+from helpers import engine_eval, oracle_eval, rel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,kw", [("cfg1", {}), ("cfg2", dict(n=24, width=16, hidden=2)), ("cfg2", dict(n=40))])
+def test_fp64_engine_matches_oracle(name, kw):
+    cfg = configs.ALL[name](**kw)
+    rep, total, terms, grad = engine_eval(cfg, np.float64)
+    L, T, G = oracle_eval(cfg, rep.flat_init_params.astype(np.float64))
+    assert abs(total - L) <= 1e-10 * abs(L)
+    np.testing.assert_allclose(terms, T, rtol=1e-10)
+    assert rel(grad, G) < 1e-9
+
+
+@pytest.mark.parametrize("name,kw", [("cfg1", {}), ("cfg2", dict(n=24, width=16, hidden=2)), ("cfg2", {})])
+def test_fp32_engine_loss_rtol_1e5(name, kw):
+    cfg = configs.ALL[name](**kw)
+    rep, total, terms, grad = engine_eval(cfg, np.float32)
+    L, T, G = oracle_eval(cfg, rep.flat_init_params.astype(np.float64))
+    assert abs(total - L) <= 1e-5 * abs(L), (total, L)
+    np.testing.assert_allclose(terms, T, rtol=1e-5)
+    assert rel(grad, G) < 2e-4
+
+
+def test_fp32_engine_vs_reference_fd_semantics():
+    """Against the reference-faithful finite-difference path in float64 (what NeuralPDE.jl
+    computes with its default eltype)."""
+    cfg = configs.config2(n=32)
+    rep, total, terms, grad = engine_eval(cfg, np.float32)
+    L, T, G = oracle_eval(cfg, rep.flat_init_params.astype(np.float64), derivative="fd")
+    assert abs(total - L) <= 1e-5 * abs(L)
+    assert rel(grad, G) < 2e-4
+
+
+def test_residual_probe_matches_oracle():
+    cfg = configs.config2(n=20, width=16, hidden=2)
+    rep, *_ = engine_eval(cfg, np.float64, want_grad=False)
+    from oracle import reference as R
+    import torch
+    prob = R.Problem(cfg.pde_system, cfg.oracle_chains(), derivative="exact")
+    pts = rep.point_sets[0]
+    r = rep.loss_functions.datafree_pde_loss_functions[0](pts, rep.flat_init_params)
+    ro = prob.residual(cfg.pde_system.eqs[0], torch.as_tensor(pts), torch.as_tensor(rep.flat_init_params)).numpy()
+    np.testing.assert_allclose(r, ro, rtol=1e-9, atol=1e-11)
+
+
+def test_term_weights_and_loss_only():
+    cfg = configs.config2(n=16, width=16, hidden=2)
+    disc = cfg.discretization(dtype=np.float64)
+    rep = npde.symbolic_discretize(cfg.pde_system, disc)
+    th = rep.flat_init_params
+    w = np.array([2.0, 0.5, 1.0, 3.0, 0.25])
+    total, terms, grad = rep.engine.loss_grad_host(th, w, True)
+    assert abs(total - float(np.dot(w, terms))) < 1e-12 * abs(total)
+    total2, terms2, g2 = rep.engine.loss_grad_host(th, w, False)
+    assert g2 is None and abs(total2 - total) < 1e-13 * abs(total)
+    # gradient is linear in the weights
+    _, _, g_a = rep.engine.loss_grad_host(th, np.array([1.0, 0, 0, 0, 0]), True)
+    _, _, g_b = rep.engine.loss_grad_host(th, np.array([0, 1.0, 1.0, 1.0, 1.0]), True)
+    _, _, g_ab = rep.engine.loss_grad_host(th, np.ones(5), True)
+    assert rel(g_a + g_b, g_ab) < 1e-12
