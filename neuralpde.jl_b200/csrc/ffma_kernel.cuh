@@ -377,7 +377,8 @@ __device__ __forceinline__ void rebuild_h(real* H, const real* stash, const DevC
 }
 
 // residual program: forward values and reverse adjoints, one point per lane (warp 0 only)
-template <typename real>
+// STRIDE = points per tile in the Xs / taps / tapbar arrays ([index][point])
+template <typename real, int STRIDE>
 __device__ __noinline__ real run_program(const DevTerm& tm, const real* theta_p, const real* Xs, const real* taps,
                                           real* tapbar, real* pbar, int lane, bool want_adjoint) {
   real val[PINN_MAX_INSTR];
@@ -387,8 +388,8 @@ __device__ __noinline__ real run_program(const DevTerm& tm, const real* theta_p,
     real v;
     switch (in.op) {
       case PINN_OP_CONST: v = real(in.imm); break;
-      case PINN_OP_COORD: v = Xs[in.a * kTilePts + lane]; break;
-      case PINN_OP_TAP: v = taps[in.a * kTilePts + lane]; break;
+      case PINN_OP_COORD: v = Xs[in.a * STRIDE + lane]; break;
+      case PINN_OP_TAP: v = taps[in.a * STRIDE + lane]; break;
       case PINN_OP_PARAM: v = theta_p[in.a]; break;
       case PINN_OP_ADD: v = val[in.a] + val[in.b]; break;
       case PINN_OP_SUB: v = val[in.a] - val[in.b]; break;
@@ -424,7 +425,7 @@ __device__ __noinline__ real run_program(const DevTerm& tm, const real* theta_p,
     const DevInstr& in = tm.prog[i];
     const real g = adj[i];
     switch (in.op) {
-      case PINN_OP_TAP: tapbar[in.a * kTilePts + lane] += g; break;
+      case PINN_OP_TAP: tapbar[in.a * STRIDE + lane] += g; break;
       case PINN_OP_PARAM: pbar[in.a] += g; break;
       case PINN_OP_ADD: adj[in.a] += g; adj[in.b] += g; break;
       case PINN_OP_SUB: adj[in.a] += g; adj[in.b] -= g; break;
@@ -595,7 +596,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffma_loss_grad_kernel(const FfmaA
       real pbar[PINN_MAX_PARAMS];
 #pragma unroll
       for (int j = 0; j < PINN_MAX_PARAMS; ++j) pbar[j] = real(0);
-      const real r = run_program<real>(tm, theta + P.param_off, Xs, taps, tapbar, pbar, lane, want_grad);
+      const real r = run_program<real, kTilePts>(tm, theta + P.param_off, Xs, taps, tapbar, pbar, lane, want_grad);
       const real w = qws[lane];
       rres[lane] = r;
       double s = (double)w * (double)r * (double)r;

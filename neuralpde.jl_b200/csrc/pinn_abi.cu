@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "dev_types.h"
+#include "tc_types.h"
 
 namespace pinn {
 size_t ffma_smem_bytes(int dtype, long long buf_elems, int w_area, bool bufs_smem);
@@ -93,6 +94,11 @@ struct pinn_engine {
   int weights_resident = 0;
   int w_area = 0, ldc = 0;
   long long buf_elems = 0, stash_per_cta = 0;
+  // tensor-core path geometry
+  int tile_pts = kTilePts;
+  int tc_split = 0, tc_tl_max = 0, tc_off_P = 0, tc_off_Q = 0, tc_off_misc = 0;
+  TcNetSmem tc_nets[PINN_MAX_NETS];
+  long long tc_stash_per_cta = 0;
   // workspaces (device)
   void* partial = nullptr;
   double* term_sums = nullptr;
@@ -134,7 +140,7 @@ static void retile(pinn_engine* e) {
   int t0 = 0;
   for (int t = 0; t < e->n_terms; ++t) {
     e->dyn[t].tile0 = t0;
-    e->dyn[t].n_tiles = (int)((e->dyn[t].n + kTilePts - 1) / kTilePts);
+    e->dyn[t].n_tiles = (int)((e->dyn[t].n + e->tile_pts - 1) / e->tile_pts);
     t0 += e->dyn[t].n_tiles;
   }
   e->total_tiles = t0;
@@ -147,8 +153,6 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
     return fail("pinn_create: descriptor abi_version %d, library %d", d->abi_version, PINN_ABI_VERSION);
   if (d->dtype != PINN_F32 && d->dtype != PINN_F64) return fail("pinn_create: unknown dtype %d", d->dtype);
   if (d->mode < PINN_MODE_FFMA || d->mode > PINN_MODE_TC_SPLIT) return fail("pinn_create: unknown mode %d", d->mode);
-  if (d->mode != PINN_MODE_FFMA)
-    return fail("pinn_create: mode %d (tcgen05) is not available in this build for this problem", d->mode);
   if (d->n_nets < 1 || d->n_nets > PINN_MAX_NETS) return fail("pinn_create: n_nets=%d out of range [1,%d]", d->n_nets, PINN_MAX_NETS);
   if (d->n_terms < 1 || d->n_terms > PINN_MAX_TERMS)
     return fail("pinn_create: n_terms=%d out of range [1,%d]", d->n_terms, PINN_MAX_TERMS);
@@ -370,8 +374,76 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       break;
     }
   }
-  if (!chosen)
-    return fail("pinn_create: a %d-wide layer panel does not fit in shared memory (%d bytes)", max_w8, max_smem);
+  if (d->mode == PINN_MODE_FFMA) {
+    if (!chosen)
+      return fail("pinn_create: a %d-wide layer panel does not fit in shared memory (%d bytes)", max_w8, max_smem);
+    return 0;
+  }
+
+  // ---- tcgen05 path: supported-shape check and shared-memory plan -----------------------------------
+  if (d->dtype != PINN_F32) return fail("pinn_create: the tcgen05 modes compute in bf16/fp32 and need dtype PINN_F32");
+  e->tc_split = d->mode == PINN_MODE_TC_SPLIT ? 1 : 0;
+  e->tile_pts = kTcPts;
+  int tl_max = 0;
+  for (int k = 0; k < d->n_nets; ++k) {
+    const DevNet& n = P.nets[k];
+    if (n.n_layers < 2) return fail("pinn_create(tc): net %d needs at least 2 Dense layers", k);
+    if (n.dims[n.n_layers] != 1) return fail("pinn_create(tc): net %d must have a 1-dimensional output", k);
+    if (n.acts[n.n_layers - 1] != PINN_ACT_IDENTITY)
+      return fail("pinn_create(tc): net %d: the last layer must be linear (identity activation)", k);
+    for (int l = 1; l < n.n_layers; ++l)
+      if (n.dims[l] % 16 != 0 || n.dims[l] < 16 || n.dims[l] > 64)
+        return fail("pinn_create(tc): net %d hidden width %d unsupported by the tcgen05 path (16, 32, 48 or 64; use "
+                    "PINN_MODE_FFMA for other shapes)", k, n.dims[l]);
+    if (n.n_layers - 2 > kTcMaxTL)
+      return fail("pinn_create(tc): net %d has %d hidden->hidden layers (max %d)", k, n.n_layers - 2, kTcMaxTL);
+    tl_max = std::max(tl_max, n.n_layers - 2);
+  }
+  int n_used_max = 1;
+  for (int t = 0; t < d->n_terms; ++t) {
+    const DevTerm& T = P.terms[t];
+    if (T.n_taps > kTcMaxTaps) return fail("pinn_create(tc): term %d has %d taps (tcgen05 path: max %d)", t, T.n_taps, kTcMaxTaps);
+    n_used_max = std::max(n_used_max, T.n_used);
+    for (int s2 = 0; s2 < T.n_used; ++s2) {
+      const DevChan& ch = T.chan[s2];
+      const int key = ch.n1 * 8 + ch.n2;
+      const int ok[] = {0, 8, 16, 24, 32, 9, 17, 25, 18};
+      bool found = false;
+      for (int v : ok) found = found || v == key;
+      if (!found || ch.C > kTcMaxC)
+        return fail("pinn_create(tc): term %d needs %d first + %d second derivative channels; the tcgen05 path "
+                    "propagates at most %d channels per network (use PINN_MODE_FFMA)", t, ch.n1, ch.n2, kTcMaxC);
+    }
+    for (int i = 0; i < T.n_taps; ++i)
+      if (T.tap_out[i] != 0) return fail("pinn_create(tc): term %d tap %d: output component must be 0", t, i);
+  }
+  e->tc_tl_max = tl_max;
+  size_t off = 0;
+  e->tc_off_P = (int)off; off += (size_t)maxC * kTileBytes;
+  e->tc_off_Q = (int)off; off += (size_t)maxC * kTileBytes;
+  for (int k = 0; k < PINN_MAX_NETS; ++k) {
+    e->tc_nets[k].fp = -1;
+    for (int l = 0; l < kTcMaxTL; ++l) e->tc_nets[k].w_hi[l] = e->tc_nets[k].w_lo[l] = 0;
+  }
+  for (int k = 0; k < d->n_nets; ++k) {
+    const int TL = P.nets[k].n_layers - 2;
+    for (int l = 0; l < TL; ++l) {
+      e->tc_nets[k].w_hi[l] = (int)off; off += 8192;
+      if (e->tc_split) { e->tc_nets[k].w_lo[l] = (int)off; off += 8192; }
+      else e->tc_nets[k].w_lo[l] = e->tc_nets[k].w_hi[l];
+    }
+  }
+  for (int k = 0; k < d->n_nets; ++k) {
+    e->tc_nets[k].fp = (int)off;
+    off += ((size_t)FP_SIZE * 4 + 15) & ~size_t(15);
+  }
+  e->tc_off_misc = (int)off;
+  off += tc_misc_bytes();
+  if (off > (size_t)max_smem)
+    return fail("pinn_create(tc): the problem needs %zu bytes of shared memory per CTA (limit %d): too many "
+                "resident weight tiles / channels for the tcgen05 path", off, max_smem);
+  e->smem = off;
+  e->tc_stash_per_cta = (long long)n_used_max * std::max(tl_max, 1) * kTcMaxC * kTileBytes;
   return 0;
 }
 
@@ -432,8 +504,12 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   const size_t g = (size_t)e->num_sms;
   TRY_OR_DESTROY(dev_alloc(&e->partial, g * (size_t)e->n_theta * e->es, e));
   TRY_OR_DESTROY(dev_alloc((void**)&e->term_sums, g * PINN_MAX_TERMS * sizeof(double), e));
-  TRY_OR_DESTROY(dev_alloc(&e->stash, g * (size_t)e->stash_per_cta * e->es, e));
-  if (!e->bufs_smem) TRY_OR_DESTROY(dev_alloc(&e->gbufs, g * 2 * (size_t)e->buf_elems * e->es, e));
+  if (e->mode == PINN_MODE_FFMA) {
+    TRY_OR_DESTROY(dev_alloc(&e->stash, g * (size_t)e->stash_per_cta * e->es, e));
+    if (!e->bufs_smem) TRY_OR_DESTROY(dev_alloc(&e->gbufs, g * 2 * (size_t)e->buf_elems * e->es, e));
+  } else {
+    TRY_OR_DESTROY(dev_alloc(&e->stash, g * (size_t)e->tc_stash_per_cta, e));
+  }
   TRY_OR_DESTROY(dev_alloc(&e->packed, ((size_t)e->n_theta + PINN_MAX_TERMS) * e->es, e));
   TRY_OR_DESTROY(dev_alloc(&e->d_theta, (size_t)e->n_theta * e->es, e));
   TRY_OR_DESTROY(dev_alloc(&e->d_grad, (size_t)e->n_theta * e->es, e));
@@ -536,6 +612,24 @@ static void fill_args(pinn_engine* e, FfmaArgs& a, const void* theta, int mode) 
   for (int t = 0; t < PINN_MAX_TERMS; ++t) a.dyn[t] = e->dyn[t];
 }
 
+// launch the fused kernel of the handle's mode over tiles [tile_begin, tile_end)
+static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_t st) {
+  if (e->mode == PINN_MODE_FFMA) {
+    CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, st));
+    return 0;
+  }
+  TcArgs t;
+  memset(&t, 0, sizeof t);
+  t.prob = a.prob; t.theta = (const float*)a.theta; t.partial = (float*)a.partial; t.term_sums = a.term_sums;
+  t.stash = (uint8_t*)e->stash; t.stash_per_cta = e->tc_stash_per_cta; t.split = e->tc_split; t.tl_max = std::max(e->tc_tl_max, 1);
+  t.tile_begin = a.tile_begin; t.tile_end = a.tile_end; t.mode = a.mode; t.resid_out = (float*)a.resid_out;
+  t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc;
+  for (int k = 0; k < PINN_MAX_NETS; ++k) t.nets[k] = e->tc_nets[k];
+  for (int k = 0; k < PINN_MAX_TERMS; ++k) { t.seed[k] = a.seed[k]; t.dyn[k] = a.dyn[k]; }
+  CUDA_TRY(tc_launch(t, grid, e->smem, st));
+  return 0;
+}
+
 int pinn_loss_grad(pinn_handle e, const void* dev_theta, const double* host_weights, void* dev_grad,
                    void* dev_term_losses, void* dev_total, void* stream) {
   if (!e) return fail("pinn_loss_grad: null handle");
@@ -554,7 +648,7 @@ int pinn_loss_grad(pinn_handle e, const void* dev_theta, const double* host_weig
   if (prepare_scales(e, host_weights, a, sw)) return 1;
   const int grid = std::min(e->num_sms, e->total_tiles);
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, st));
-  CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, st));
+  if (launch_fused(e, a, grid, st)) return 1;
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
   e->launches += 1;
   if (e->nranks > 1) {
@@ -619,7 +713,7 @@ int pinn_term_residual(pinn_handle e, int32_t term, const void* dev_theta, void*
   a.tile_end = e->dyn[term].tile0 + e->dyn[term].n_tiles;
   a.resid_out = dev_r;
   const int grid = std::min(e->num_sms, e->dyn[term].n_tiles);
-  CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, (cudaStream_t)stream));
+  if (launch_fused(e, a, grid, (cudaStream_t)stream)) return 1;
   e->launches += 1;
   return 0;
 }

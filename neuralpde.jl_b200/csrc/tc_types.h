@@ -1,0 +1,53 @@
+// tc_types.h -- constants and launch arguments of the tcgen05 path, shared by the kernel and
+// the host ABI layer.
+#pragma once
+#include <stdint.h>
+#include "dev_types.h"
+
+namespace pinn {
+
+constexpr int kTcPts = 128;
+constexpr int kTcThreads = 256;
+constexpr int kTcMaxC = 5;
+constexpr int kTcMaxTaps = 6;
+constexpr int kTcMaxTL = 6;            // tensor (hidden->hidden) layers per network
+constexpr int kTileBytes = 16384;      // 128 rows x 128 bytes
+// fp32 parameter block per network (floats)
+constexpr int FP_W1 = 0;               // [64][8] first-layer weight, W1[o*8 + k]
+constexpr int FP_B1 = 512;             // [64]
+constexpr int FP_BT = 576;             // [kTcMaxTL][64] tensor-layer biases
+constexpr int FP_WL = FP_BT + kTcMaxTL * 64;   // [64] last-layer weight
+constexpr int FP_BL = FP_WL + 64;      // [1]
+constexpr int FP_SIZE = FP_BL + 4;
+// TMEM columns
+constexpr uint32_t TM_X = 0;           // [c][64]: forward accumulators / adjoints of layer outputs
+constexpr uint32_t TM_Y = 320;         // [c][32] recompute group, or [64] weight-gradient accumulator
+
+struct TcNetSmem {
+  int w_hi[kTcMaxTL];   // byte offsets of the bf16 weight tiles
+  int w_lo[kTcMaxTL];
+  int fp;               // byte offset of the fp32 parameter block
+};
+
+struct TcArgs {
+  const DevProblem* prob;
+  const float* theta;
+  float* partial;         // [grid][n_theta]
+  double* term_sums;      // [grid][PINN_MAX_TERMS]
+  uint8_t* stash;         // [grid][stash_per_cta] operand-tile images of every tensor layer's input
+  long long stash_per_cta;
+  int split;              // forward hi/lo split
+  int tl_max;             // max tensor layers over networks (stash indexing)
+  int tile_begin, tile_end;
+  int mode;               // 0 loss+grad, 1 loss only, 2 residual out
+  float* resid_out;
+  int off_P, off_Q, off_misc;   // byte offsets into dynamic shared memory
+  TcNetSmem nets[PINN_MAX_NETS];
+  double seed[PINN_MAX_TERMS];
+  TermDyn dyn[PINN_MAX_TERMS];
+};
+
+size_t tc_misc_bytes();
+cudaError_t tc_launch(const TcArgs& a, int grid, size_t smem, cudaStream_t st);
+
+}  // namespace pinn

@@ -381,7 +381,7 @@ class Problem:
         theta = torch.tensor(np.asarray(theta_np, dtype=np.float64), requires_grad=True)
         total, terms = self.full_loss(theta, pde_sets, bc_sets, **kw)
         (g,) = torch.autograd.grad(total, theta)
-        return float(total), np.array([float(t) for t in terms]), g.numpy().copy()
+        return float(total.detach()), np.array([float(t.detach()) for t in terms]), g.numpy().copy()
 
     def data_loss(self, depvar: str, X: np.ndarray, y: np.ndarray):
         """``mean(abs2, u_k(X) .- y)`` as an additional_loss closure."""
