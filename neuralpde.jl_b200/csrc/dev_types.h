@@ -37,6 +37,7 @@ struct DevChan {
   int s_a[PINN_MAX_CH], s_b[PINN_MAX_CH];   // indices into dir1[] (0-based)
   int rows[PINN_MAX_IN];                    // point row feeding network input j
   int stash_off[PINN_MAX_LAYERS];           // per-layer offset (scalars) inside the CTA stash
+  int pure;                                 // every second-derivative channel s is d2/d(dir1[s])^2
 };
 
 struct DevTerm {

@@ -277,6 +277,27 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
         }
       }
     }
+    // canonical channel order: directions that carry a pure second derivative come first, so that
+    // (when every second-derivative channel is pure) channel n1+1+s is d2/d(dir1[s])^2
+    for (int s = 0; s < T.n_used; ++s) {
+      DevChan& ch = T.chan[s];
+      int order[PINN_MAX_IN], inv[PINN_MAX_IN], n = 0;
+      bool used[PINN_MAX_IN] = {false};
+      for (int q = 0; q < ch.n2; ++q)
+        if (ch.s_a[q] == ch.s_b[q] && !used[ch.s_a[q]]) { order[n++] = ch.s_a[q]; used[ch.s_a[q]] = true; }
+      const int npure = n;
+      for (int j = 0; j < ch.n1; ++j) if (!used[j]) order[n++] = j;
+      int nd[PINN_MAX_IN];
+      for (int i = 0; i < ch.n1; ++i) { nd[i] = ch.dir1[order[i]]; inv[order[i]] = i; }
+      for (int i = 0; i < ch.n1; ++i) ch.dir1[i] = nd[i];
+      for (int q = 0; q < ch.n2; ++q) {
+        int a = inv[ch.s_a[q]], b = inv[ch.s_b[q]];
+        if (a > b) std::swap(a, b);
+        ch.s_a[q] = a; ch.s_b[q] = b;
+      }
+      ch.pure = (npure == ch.n2) ? 1 : 0;
+      if (ch.pure) for (int q = 0; q < ch.n2; ++q) ch.s_a[q] = ch.s_b[q] = q;
+    }
     long long stash = 0;
     for (int s = 0; s < T.n_used; ++s) {
       DevChan& ch = T.chan[s];
@@ -439,7 +460,7 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
   }
   e->tc_off_misc = (int)off;
   off += tc_misc_bytes();
-  if (off > (size_t)max_smem)
+  if (off + 1024 > (size_t)max_smem)   // + the kernel's static shared memory
     return fail("pinn_create(tc): the problem needs %zu bytes of shared memory per CTA (limit %d): too many "
                 "resident weight tiles / channels for the tcgen05 path", off, max_smem);
   e->smem = off;
@@ -624,7 +645,15 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
   t.stash = (uint8_t*)e->stash; t.stash_per_cta = e->tc_stash_per_cta; t.split = e->tc_split; t.tl_max = std::max(e->tc_tl_max, 1);
   t.tile_begin = a.tile_begin; t.tile_end = a.tile_end; t.mode = a.mode; t.resid_out = (float*)a.resid_out;
   t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc;
-  for (int k = 0; k < PINN_MAX_NETS; ++k) t.nets[k] = e->tc_nets[k];
+  for (int k = 0; k < PINN_MAX_NETS; ++k) {
+    t.nets[k] = e->tc_nets[k];
+    int ak = 1;
+    if (k < e->hprob->n_nets) {
+      const DevNet& n = e->hprob->nets[k];
+      for (int l = 0; l + 1 < n.n_layers; ++l) if (n.acts[l] != PINN_ACT_TANH) ak = 0;
+    }
+    t.net_ak[k] = ak;
+  }
   for (int k = 0; k < PINN_MAX_TERMS; ++k) { t.seed[k] = a.seed[k]; t.dyn[k] = a.dyn[k]; }
   CUDA_TRY(tc_launch(t, grid, e->smem, st));
   return 0;

@@ -29,6 +29,8 @@
 namespace pinn {
 
 // ---- small helpers ---------------------------------------------------------------------------------
+constexpr int kNH = kTcThreads / 128;   // warps per TMEM lane quadrant: each takes 1/kNH of the columns
+
 template <int N>
 __device__ __forceinline__ float pick(const float* v, int idx) {
   float r = v[0];
@@ -42,384 +44,652 @@ __device__ __forceinline__ void add_at(float* v, int idx, float x) {
   for (int i = 0; i < N; ++i) v[i] += (idx == i) ? x : 0.f;
 }
 
-__device__ __forceinline__ float bf16_hi(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// activation value and first three derivatives.  AK = 1: tanh, 2: sigmoid (branch-free, built on
+// ex2.approx + rcp.approx: absolute error ~1e-7, far below the bf16-split operand noise);
+// AK = 0: any activation through the accurate generic evaluator.
+template <int AK>
+__device__ __forceinline__ void act_eval_tc(int act, float z, float& a, float& d1, float& d2, float& d3) {
+  if (AK == 1) {
+    const float e = __expf(2.f * z);
+    const float t = 1.f - __fdividef(2.f, e + 1.f);
+    const float s = fmaf(-t, t, 1.f);
+    a = t; d1 = s; d2 = -2.f * t * s; d3 = s * fmaf(6.f * t, t, -2.f);
+  } else if (AK == 2) {
+    const float g = __fdividef(1.f, 1.f + __expf(-z));
+    const float g1 = g * (1.f - g);
+    a = g; d1 = g1; d2 = g1 * fmaf(-2.f, g, 1.f); d3 = g1 * fmaf(-6.f, g1, 1.f);
+  } else {
+    act_eval<float>(act, z, a, d1, d2, d3);
+  }
+}
+__device__ __forceinline__ int act_kind(int act) { return act == PINN_ACT_TANH ? 1 : (act == PINN_ACT_SIGMOID ? 2 : 0); }
 
-// store 8 consecutive columns (one 16-byte chunk) of a row into a swizzled tile, hi and optionally lo
-__device__ __forceinline__ void store_chunk(uint8_t* tile_hi, uint8_t* tile_lo, int row, int chunk, const float (&v)[8],
-                                            bool split) {
-  const uint32_t off = tc::swz_chunk(row, chunk);
-  uint4 h;
+// store 4 consecutive columns (half of a 16-byte chunk) of a row into a swizzled tile; with `split`
+// also the bf16 residual v - bf16(v) into the lo tile
+__device__ __forceinline__ void store_half(uint8_t* tile_hi, uint8_t* tile_lo, int row, int col0, const float (&v)[4],
+                                           bool split) {
+  const uint32_t off = tc::swz_chunk(row, col0 >> 3) + ((col0 & 4) << 1);
+  uint2 h;
   h.x = tc::pack_bf16(v[0], v[1]); h.y = tc::pack_bf16(v[2], v[3]);
-  h.z = tc::pack_bf16(v[4], v[5]); h.w = tc::pack_bf16(v[6], v[7]);
-  *reinterpret_cast<uint4*>(tile_hi + off) = h;
+  *reinterpret_cast<uint2*>(tile_hi + off) = h;
   if (split) {
-    float r[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) r[i] = v[i] - bf16_hi(v[i]);
-    uint4 l;
-    l.x = tc::pack_bf16(r[0], r[1]); l.y = tc::pack_bf16(r[2], r[3]);
-    l.z = tc::pack_bf16(r[4], r[5]); l.w = tc::pack_bf16(r[6], r[7]);
-    *reinterpret_cast<uint4*>(tile_lo + off) = l;
+    uint2 l;
+    l.x = tc::pack_bf16(v[0] - __uint_as_float(h.x << 16), v[1] - __uint_as_float(h.x & 0xffff0000u));
+    l.y = tc::pack_bf16(v[2] - __uint_as_float(h.y << 16), v[3] - __uint_as_float(h.y & 0xffff0000u));
+    *reinterpret_cast<uint2*>(tile_lo + off) = l;
   }
 }
 
-__device__ __forceinline__ float load_bf16(const uint8_t* tile, int row, int col) {
-  const __nv_bfloat16 b = *reinterpret_cast<const __nv_bfloat16*>(tile + tc::swz_off(row, col));
-  return __bfloat162float(b);
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// channel bookkeeping of one (term, network): value + N1 first + N2 second derivative channels
+// channel bookkeeping of one (term, network): value + N1 first + N2 second derivative channels.
+// PURE: second-derivative channel s is d2/dx_s^2 of first-derivative channel s (no index selects).
 template <int N1, int N2>
 struct Chan {
-  static constexpr int C = 1 + N1 + N2;
   int sa[N2 > 0 ? N2 : 1], sb[N2 > 0 ? N2 : 1];
 };
 
 // post-activation channels from pre-activation channels (z[0] value, z[1..N1], z[1+N1..])
-template <int N1, int N2>
+template <int N1, int N2, bool PURE, int AK>
 __device__ __forceinline__ void chain_fwd(int act, const Chan<N1, N2>& ch, const float* z, float* h) {
   constexpr int M1 = (N1 > 0) ? N1 : 1;
   float a, d1, d2, d3;
-  act_eval<float>(act, z[0], a, d1, d2, d3);
+  act_eval_tc<AK>(act, z[0], a, d1, d2, d3);
   h[0] = a;
 #pragma unroll
   for (int i = 0; i < N1; ++i) h[1 + i] = d1 * z[1 + i];
 #pragma unroll
   for (int s = 0; s < N2; ++s) {
-    const float za = pick<M1>(z + 1, ch.sa[s]), zb = pick<M1>(z + 1, ch.sb[s]);
-    h[1 + N1 + s] = d1 * z[1 + N1 + s] + d2 * za * zb;
+    const float za = PURE ? z[1 + (s < N1 ? s : 0)] : pick<M1>(z + 1, ch.sa[s]);
+    const float zb = PURE ? za : pick<M1>(z + 1, ch.sb[s]);
+    h[1 + N1 + s] = fmaf(d1, z[1 + N1 + s], d2 * za * zb);
   }
 }
 
 // adjoints of pre-activations from adjoints of post-activations
-template <int N1, int N2>
+template <int N1, int N2, bool PURE, int AK>
 __device__ __forceinline__ void chain_bwd(int act, const Chan<N1, N2>& ch, const float* z, const float* hb, float* zb) {
   constexpr int M1 = (N1 > 0) ? N1 : 1;
   float a, d1, d2, d3;
-  act_eval<float>(act, z[0], a, d1, d2, d3);
+  act_eval_tc<AK>(act, z[0], a, d1, d2, d3);
   float acc0 = d1 * hb[0];
 #pragma unroll
   for (int i = 0; i < N1; ++i) {
-    acc0 += d2 * z[1 + i] * hb[1 + i];
+    acc0 = fmaf(d2 * z[1 + i], hb[1 + i], acc0);
     zb[1 + i] = d1 * hb[1 + i];
   }
 #pragma unroll
   for (int s = 0; s < N2; ++s) {
-    const float za = pick<M1>(z + 1, ch.sa[s]), zbb = pick<M1>(z + 1, ch.sb[s]);
     const float g = hb[1 + N1 + s];
-    acc0 += (d2 * z[1 + N1 + s] + d3 * za * zbb) * g;
-    add_at<M1>(zb + 1, ch.sa[s], d2 * zbb * g);
-    add_at<M1>(zb + 1, ch.sb[s], d2 * za * g);
+    if (PURE) {
+      const int i = s < N1 ? s : 0;
+      const float za = z[1 + i];
+      acc0 = fmaf(fmaf(d2, z[1 + N1 + s], d3 * za * za), g, acc0);
+      zb[1 + i] = fmaf(2.f * d2 * za, g, zb[1 + i]);
+    } else {
+      const float za = pick<M1>(z + 1, ch.sa[s]), zbb = pick<M1>(z + 1, ch.sb[s]);
+      acc0 = fmaf(fmaf(d2, z[1 + N1 + s], d3 * za * zbb), g, acc0);
+      add_at<M1>(zb + 1, ch.sa[s], d2 * zbb * g);
+      add_at<M1>(zb + 1, ch.sb[s], d2 * za * g);
+    }
     zb[1 + N1 + s] = d1 * g;
   }
   zb[0] = acc0;
 }
 
-// everything a tile phase needs, gathered once
-struct TileCtx {
-  uint8_t* smem;
-  uint8_t *P, *Q;
-  float *Xs, *taps, *tapbar, *qws, *rres, *scratch;
-  double* tsum;
-  uint64_t *bar_mma, *bar_ld;
+// sum over the 32 lanes of 4 per-lane values with 6 shuffles.  Every lane receives the total of
+// element e = ((lane>>4)&1)*2 + ((lane>>3)&1); lanes with (lane & 7) == 0 act on it.
+__device__ __forceinline__ float warp_reduce4(const float (&v)[4], int lane) {
+  const bool up16 = (lane & 16) != 0;
+  float a0 = (up16 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[2], 16);
+  float a1 = (up16 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, up16 ? v[1] : v[3], 16);
+  const bool up8 = (lane & 8) != 0;
+  float r = (up8 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, up8 ? a0 : a1, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+__device__ __forceinline__ int reduce4_elem(int lane) { return ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1); }
+
+// CTA-wide constants kept in shared memory so the per-network passes (separate functions) do not
+// drag a context struct through local memory
+struct CtaShared {
   uint32_t tmem;
-  uint32_t mma_phase, ld_phase;
-  int tid, warp, lane, q, hh, p;
-  uint32_t lane_addr;   // (q*32) << 16
+  int split, tl_max, off_P, off_Q, off_misc;
+  float* partial;
+  uint8_t* stash;
+  const float* theta;
+  TcNetSmem nets[PINN_MAX_NETS];
 };
 
-__device__ __forceinline__ void wait_mma(TileCtx& cx) {
-  tc::mbar_wait(cx.bar_mma, cx.mma_phase);
-  cx.mma_phase ^= 1u;
-  tc::tc_fence_after();
+struct Misc {   // carve-up of the misc region
+  float *Xs, *taps, *tapbar, *scratch, *qws, *rres;
+  double* tsum;
+  uint64_t *bar_mma, *bar_ld;
+  uint32_t* tmem_slot;
+};
+__device__ __forceinline__ Misc misc_of(uint8_t* m) {
+  Misc r;
+  r.Xs = reinterpret_cast<float*>(m);             m += PINN_MAX_DIM * kTcPts * 4;
+  r.taps = reinterpret_cast<float*>(m);           m += kTcMaxTaps * kTcPts * 4;
+  r.tapbar = reinterpret_cast<float*>(m);         m += kTcMaxTaps * kTcPts * 4;
+  r.scratch = reinterpret_cast<float*>(m);        m += kTcMaxC * kTcPts * 4;
+  r.qws = reinterpret_cast<float*>(m);            m += kTcPts * 4;
+  r.rres = reinterpret_cast<float*>(m);           m += kTcPts * 4;
+  r.tsum = reinterpret_cast<double*>(m);          m += PINN_MAX_TERMS * 8;
+  r.bar_mma = reinterpret_cast<uint64_t*>(m);     m += 8;
+  r.bar_ld = reinterpret_cast<uint64_t*>(m);      m += 8;
+  r.tmem_slot = reinterpret_cast<uint32_t*>(m);
+  return r;
 }
 
-// first layer pre-activations of 8 neurons [o0, o0+8): z[c][i]
+// descriptor fields a network pass needs, read once from global memory into registers
 template <int N1, int N2>
-__device__ __forceinline__ void first_layer_z(const float* fp, const DevChan& dc, const float* x /*[d]*/, int d_in, int o0,
-                                              float (&z)[1 + N1 + N2][8]) {
+struct PassInfo {
+  int L, TL, d_in, n1w, nL;
+  int dir1[N1 > 0 ? N1 : 1];
+  Chan<N1, N2> ch;
+};
+template <int N1, int N2>
+__device__ __forceinline__ void load_pass(PassInfo<N1, N2>& pi, const DevNet& net, const DevChan& dc) {
+  pi.L = net.n_layers; pi.TL = pi.L - 2; pi.d_in = net.dims[0]; pi.n1w = net.dims[1]; pi.nL = net.dims[pi.L - 1];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int o = o0 + i;
-    float s = fp[FP_B1 + o];
+  for (int j = 0; j < N1; ++j) pi.dir1[j] = dc.dir1[j];
 #pragma unroll
-    for (int k = 0; k < PINN_MAX_IN; ++k)
-      if (k < d_in) s = fmaf(fp[FP_W1 + o * 8 + k], x[k], s);
-    z[0][i] = s;
+  for (int s = 0; s < N2; ++s) { pi.ch.sa[s] = dc.s_a[s]; pi.ch.sb[s] = dc.s_b[s]; }
+}
+
+// first-layer pre-activations of neuron o (channel vector zz)
+template <int N1, int N2>
+__device__ __forceinline__ void first_layer_elem(const float* fp, const PassInfo<N1, N2>& pi, const float (&x)[PINN_MAX_IN],
+                                                 int o, float* zz) {
+  float s = fp[FP_B1 + o];
 #pragma unroll
-    for (int j = 0; j < N1; ++j) z[1 + j][i] = fp[FP_W1 + o * 8 + dc.dir1[j]];
+  for (int k = 0; k < PINN_MAX_IN; ++k)
+    if (k < pi.d_in) s = fmaf(fp[FP_W1 + o * 8 + k], x[k], s);
+  zz[0] = s;
 #pragma unroll
-    for (int j = 0; j < N2; ++j) z[1 + N1 + j][i] = 0.f;
+  for (int j = 0; j < N1; ++j) zz[1 + j] = fp[FP_W1 + o * 8 + pi.dir1[j]];
+#pragma unroll
+  for (int j = 0; j < N2; ++j) zz[1 + N1 + j] = 0.f;
+}
+
+__device__ __forceinline__ void wait_bar(uint64_t* bar, uint32_t& phase) {
+  tc::mbar_wait(bar, phase);
+  phase ^= 1u;
+}
+
+// issue a chain of nk MMAs D (+)= A_k * B_k; descriptors advance by a_step / b_step bytes per k-step
+__device__ __forceinline__ void mma_chain(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t a_step, uint32_t b_step, int nk,
+                                          uint32_t idesc, uint32_t acc_first) {
+  const uint64_t da = a_step >> 4, db = b_step >> 4;
+#pragma unroll 1
+  for (int k = 0; k < nk; ++k) {
+    tc::mma_bf16(d, adesc, bdesc, idesc, (k > 0) ? 1u : acc_first);
+    adesc += da;
+    bdesc += db;
+  }
+}
+
+// thread identity inside the CTA
+struct Tid {
+  int tid, warp, lane, q, hh, p;
+  uint32_t lane_addr;
+};
+__device__ __forceinline__ Tid tid_of() {
+  Tid t;
+  t.tid = threadIdx.x; t.warp = t.tid >> 5; t.lane = t.tid & 31; t.q = t.warp & 3; t.hh = t.warp >> 2;
+  t.p = t.q * 32 + t.lane;
+  t.lane_addr = (uint32_t)(t.q * 32) << 16;
+  return t;
+}
+
+// ---- granule loops (4 columns x all channels per step), specialised on the activation kind -------------
+// (inlined into the per-network passes; a noinline callee only gets the ABI scratch registers and spills)
+struct LoopCtx {
+  const float* fp;        // fp32 parameter block of the network (shared memory)
+  const float* bt;        // bias of the current tensor layer
+  uint8_t* tP;            // hi operand tiles
+  uint8_t* tQ;            // lo operand tiles (forward split)
+  float* gb;              // bias gradient of the current layer (CTA partial)
+  float* gw;              // weight gradient of the first layer (CTA partial)
+  uint32_t taddr;         // tmem base + lane quadrant
+  int act, split, p, lane, g0, g1, c0, flag;
+};
+
+// layer 0 forward: coordinates -> H^0 tiles (+ last-layer dot when there is no tensor layer: flag)
+template <int N1, int N2, bool PURE, int AK>
+__device__ __forceinline__ void l0_fwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, const float* xp, float* up) {
+  constexpr int C = 1 + N1 + N2;
+  const LoopCtx& lc = *lcp;
+  const PassInfo<N1, N2>& pi = *pip;
+  float x[PINN_MAX_IN], u[C];
+#pragma unroll
+  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = xp[k];
+#pragma unroll
+  for (int c = 0; c < C; ++c) u[c] = up[c];
+#pragma unroll 1
+  for (int g = lc.g0; g < lc.g1; ++g) {
+    float h[C][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float zz[C], hv[C];
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * 4 + i, zz);
+      chain_fwd<N1, N2, PURE, AK>(lc.act, pi.ch, zz, hv);
+#pragma unroll
+      for (int c = 0; c < C; ++c) h[c][i] = hv[c];
+      if (lc.flag) {
+        const float wl = lc.fp[FP_WL + g * 4 + i];
+#pragma unroll
+        for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tQ + c * kTileBytes, lc.p, g * 4, h[c], lc.split != 0);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) up[c] = u[c];
+}
+
+// tensor layer forward epilogue: TMEM accumulators -> bias + activation chain -> next operand tiles
+template <int N1, int N2, bool PURE, int AK>
+__device__ __forceinline__ void tl_fwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, float* up) {
+  constexpr int C = 1 + N1 + N2;
+  const LoopCtx& lc = *lcp;
+  const Chan<N1, N2>& ch = pip->ch;
+  float u[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) u[c] = up[c];
+#pragma unroll 1
+  for (int g = lc.g0; g < lc.g1; ++g) {
+    float z[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_X + c * 64 + g * 4, z[c]);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float zz[C], hv[C];
+      zz[0] = z[0][i] + lc.bt[g * 4 + i];
+#pragma unroll
+      for (int c = 1; c < C; ++c) zz[c] = z[c][i];
+      chain_fwd<N1, N2, PURE, AK>(lc.act, ch, zz, hv);
+#pragma unroll
+      for (int c = 0; c < C; ++c) z[c][i] = hv[c];
+      if (lc.flag) {
+        const float wl = lc.fp[FP_WL + g * 4 + i];
+#pragma unroll
+        for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tQ + c * kTileBytes, lc.p, g * 4, z[c], lc.split != 0);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c) up[c] = u[c];
+}
+
+// tensor layer backward epilogue for the column group starting at c0: recomputed Z (TMEM Y) and output
+// adjoints (TMEM X, or w_last * ubar for the last hidden layer: flag) -> Zbar tiles + bias gradient
+template <int N1, int N2, bool PURE, int AK>
+__device__ __forceinline__ void tl_bwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, const float* ubp) {
+  constexpr int C = 1 + N1 + N2;
+  const LoopCtx& lc = *lcp;
+  const Chan<N1, N2>& ch = pip->ch;
+  float ub[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) ub[c] = ubp[c];
+  const int re = reduce4_elem(lc.lane);
+  const bool rlead = (lc.lane & 7) == 0;
+#pragma unroll 1
+  for (int g = lc.g0; g < lc.g1; ++g) {
+    const int ocol = lc.c0 + g * 4;
+    float z[C][4], hb[C][4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_Y + c * 32 + g * 4, z[c]);
+    if (!lc.flag) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_X + c * 64 + ocol, hb[c]);
+    }
+    tc::tmem_ld_wait();
+    if (lc.flag) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float wl = lc.fp[FP_WL + ocol + i];
+#pragma unroll
+        for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
+      }
+    }
+    float zb0[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float zz[C], hv[C], zv[C];
+      zz[0] = z[0][i] + lc.bt[ocol + i];
+#pragma unroll
+      for (int c = 1; c < C; ++c) zz[c] = z[c][i];
+#pragma unroll
+      for (int c = 0; c < C; ++c) hv[c] = hb[c][i];
+      chain_bwd<N1, N2, PURE, AK>(lc.act, ch, zz, hv, zv);
+#pragma unroll
+      for (int c = 0; c < C; ++c) hb[c][i] = zv[c];
+      zb0[i] = zv[0];
+    }
+    const float bs = warp_reduce4(zb0, lc.lane);
+    if (rlead) atomicAdd(lc.gb + ocol + re, bs);
+#pragma unroll
+    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tP, lc.p, ocol, hb[c], false);
+  }
+}
+
+// layer 0 backward: adjoints of H^0 (TMEM X, or w_last * ubar: flag) -> first-layer weight / bias gradient
+template <int N1, int N2, bool PURE, int AK>
+__device__ __forceinline__ void l0_bwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, const float* xp, const float* ubp) {
+  constexpr int C = 1 + N1 + N2;
+  const LoopCtx& lc = *lcp;
+  const PassInfo<N1, N2>& pi = *pip;
+  float x[PINN_MAX_IN], ub[C];
+#pragma unroll
+  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = xp[k];
+#pragma unroll
+  for (int c = 0; c < C; ++c) ub[c] = ubp[c];
+  const int re = reduce4_elem(lc.lane);
+  const bool rlead = (lc.lane & 7) == 0;
+  const int n1w = pi.n1w;
+#pragma unroll 1
+  for (int g = lc.g0; g < lc.g1; ++g) {
+    float hb[C][4];
+    if (!lc.flag) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_X + c * 64 + g * 4, hb[c]);
+      tc::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float wl = lc.fp[FP_WL + g * 4 + i];
+#pragma unroll
+        for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
+      }
+    }
+    float zv0[4], zvd[N1 > 0 ? N1 : 1][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float zz[C], hv[C], zv[C];
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * 4 + i, zz);
+#pragma unroll
+      for (int c = 0; c < C; ++c) hv[c] = hb[c][i];
+      chain_bwd<N1, N2, PURE, AK>(lc.act, pi.ch, zz, hv, zv);
+      zv0[i] = zv[0];
+#pragma unroll
+      for (int jd = 0; jd < N1; ++jd) zvd[jd][i] = zv[1 + jd];
+    }
+    // Wbar_0[o][k] = sum_p zbar_0 x_k + zbar_(channel of direction k);  bbar_0[o] = sum_p zbar_0
+    const float bs = warp_reduce4(zv0, lc.lane);
+    if (rlead) atomicAdd(lc.gb + g * 4 + re, bs);
+#pragma unroll
+    for (int k = 0; k < PINN_MAX_IN; ++k) {
+      if (k < pi.d_in) {
+        float gk[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float gg = zv0[i] * x[k];
+#pragma unroll
+          for (int jd = 0; jd < N1; ++jd) gg += (pi.dir1[jd] == k) ? zvd[jd][i] : 0.f;
+          gk[i] = gg;
+        }
+        const float gs = warp_reduce4(gk, lc.lane);
+        if (rlead) atomicAdd(lc.gw + g * 4 + re + (long long)n1w * k, gs);
+      }
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// forward + backward of one network for the current tile, channel structure <N1, N2>
-template <int N1, int N2>
-__device__ __noinline__ void net_forward(TileCtx& cx, const TcArgs& args, const DevProblem& P, const DevTerm& tm, int slot,
-                                         bool want_grad, uint8_t* stash) {
+// forward of one network for the current tile, channel structure <N1, N2, PURE>.
+// `phase` bit 0 = parity of the MMA barrier, bit 1 = parity of the bulk-load barrier; returned updated.
+template <int N1, int N2, bool PURE, int AK>
+__device__ __noinline__ uint32_t net_forward(const CtaShared* cs, const DevProblem* Pp, const DevTerm* tmp, int slot,
+                                             int want_grad, uint32_t phase) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int C = 1 + N1 + N2;
+  const DevTerm& tm = *tmp;
   const int net_id = tm.used_net[slot];
-  const DevNet& net = P.nets[net_id];
+  const DevNet& net = Pp->nets[net_id];
   const DevChan& dc = tm.chan[slot];
-  const TcNetSmem& ns = args.nets[net_id];
-  const float* fp = reinterpret_cast<const float*>(cx.smem + ns.fp);
-  const int L = net.n_layers;
-  const int d_in = net.dims[0];
-  const int TL = L - 2;                         // tensor layers 1..L-2
-  const bool split = args.split != 0;
-  Chan<N1, N2> ch;
-#pragma unroll
-  for (int s = 0; s < N2; ++s) { ch.sa[s] = dc.s_a[s]; ch.sb[s] = dc.s_b[s]; }
-  const int p = cx.p, hh = cx.hh, tid = cx.tid;
+  const TcNetSmem ns = cs->nets[net_id];
+  const float* fp = reinterpret_cast<const float*>(smem + ns.fp);
+  uint8_t* tP = smem + cs->off_P;
+  uint8_t* tQ = smem + cs->off_Q;
+  const Misc ms = misc_of(smem + cs->off_misc);
+  const uint32_t tmem = cs->tmem;
+  const bool split = cs->split != 0;
+  PassInfo<N1, N2> pi;
+  load_pass<N1, N2>(pi, net, dc);
+  const int TL = pi.TL;
+  const Tid t = tid_of();
+  const int tid = t.tid, hh = t.hh, p = t.p;
+  uint32_t mma_phase = phase & 1u;
   float x[PINN_MAX_IN];
 #pragma unroll
-  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < d_in) ? cx.Xs[dc.rows[k] * kTcPts + p] : 0.f;
-  uint8_t* stash_slot = stash + (size_t)slot * args.tl_max * kTcMaxC * kTileBytes;
+  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < pi.d_in) ? ms.Xs[dc.rows[k] * kTcPts + p] : 0.f;
+  uint8_t* stash_slot = cs->stash + (size_t)slot * cs->tl_max * kTcMaxC * kTileBytes;
 
+  float u[C];                                   // last-layer partial dot products of this thread
+#pragma unroll
+  for (int c = 0; c < C; ++c) u[c] = 0.f;
+  // the cross-warp combination of u goes through shared-memory atomics
+  if (tid < C * kTcPts / 4) reinterpret_cast<float4*>(ms.scratch)[tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (kTcThreads < C * kTcPts / 4 && tid + kTcThreads < C * kTcPts / 4)
+    reinterpret_cast<float4*>(ms.scratch)[tid + kTcThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
   {
-    // =============================== FORWARD ==========================================================
-    float u[C];                                   // last-layer partial dot products of this thread
-#pragma unroll
-    for (int c = 0; c < C; ++c) u[c] = 0.f;
-    {
-      // ---- layer 0 on the CUDA cores ------------------------------------------------------------------
-      const int n1w = net.dims[1];
-      const int nch = n1w / 8, c0 = hh * (nch / 2), c1 = (hh + 1) * (nch / 2);
-      for (int j = c0; j < c1; ++j) {
-        float z[C][8], h[C][8];
-        first_layer_z<N1, N2>(fp, dc, x, d_in, j * 8, z);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float zz[C], hv[C];
-#pragma unroll
-          for (int c = 0; c < C; ++c) zz[c] = z[c][i];
-          chain_fwd<N1, N2>(net.acts[0], ch, zz, hv);
-#pragma unroll
-          for (int c = 0; c < C; ++c) h[c][i] = hv[c];
-          if (TL == 0) {
-            const float wl = fp[FP_WL + j * 8 + i];
-#pragma unroll
-            for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-          store_chunk(cx.P + c * kTileBytes, cx.Q + c * kTileBytes, p, j, h[c], split);
-      }
-    }
-    // ---- tensor layers -------------------------------------------------------------------------------------
-    for (int l = 1; l <= TL; ++l) {
-      const int n_in = net.dims[l], n_out = net.dims[l + 1];
-      tc::fence_async_smem();
-      tc::tc_fence_before();
-      __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        if (want_grad) {
-          for (int c = 0; c < C; ++c)
-            tc::bulk_store(stash_slot + (size_t)((l - 1) * kTcMaxC + c) * kTileBytes, cx.P + c * kTileBytes, kTileBytes);
-          tc::bulk_commit();
-        }
-        const uint32_t idesc = tc::make_idesc(128, n_out, 0, 0);
-        const uint32_t whi = tc::smem_u32(cx.smem + ns.w_hi[l - 1]), wlo = tc::smem_u32(cx.smem + ns.w_lo[l - 1]);
-        for (int c = 0; c < C; ++c) {
-          const uint32_t ahi = tc::smem_u32(cx.P + c * kTileBytes), alo = tc::smem_u32(cx.Q + c * kTileBytes);
-          const uint32_t d = cx.tmem + TM_X + c * 64;
-          uint32_t acc = 0;
-          for (int k = 0; k < n_in / 16; ++k) {
-            tc::mma_bf16(d, tc::make_desc(ahi + k * 32, 0, 1024), tc::make_desc(whi + k * 32, 0, 1024), idesc, acc);
-            acc = 1;
-          }
-          if (split) {
-            for (int k = 0; k < n_in / 16; ++k)
-              tc::mma_bf16(d, tc::make_desc(ahi + k * 32, 0, 1024), tc::make_desc(wlo + k * 32, 0, 1024), idesc, 1);
-            for (int k = 0; k < n_in / 16; ++k)
-              tc::mma_bf16(d, tc::make_desc(alo + k * 32, 0, 1024), tc::make_desc(whi + k * 32, 0, 1024), idesc, 1);
-          }
-        }
-        tc::mma_commit(cx.bar_mma);
-      }
-      wait_mma(cx);
-      if (tid == 0 && want_grad) tc::bulk_wait_read0();   // stash copies have finished reading P
-      __syncthreads();
-      // ---- epilogue: TMEM -> bias + activation chain -> next operand tiles ------------------------------------
-      const int nch = n_out / 8, c0 = hh * (nch / 2), c1 = (hh + 1) * (nch / 2);
-      for (int j = c0; j < c1; ++j) {
-        float z[C][8], h[C][8];
-#pragma unroll
-        for (int c = 0; c < C; ++c) tc::tmem_ld8(cx.tmem + cx.lane_addr + TM_X + c * 64 + j * 8, z[c]);
-        tc::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float zz[C], hv[C];
-          zz[0] = z[0][i] + fp[FP_BT + (l - 1) * 64 + j * 8 + i];
-#pragma unroll
-          for (int c = 1; c < C; ++c) zz[c] = z[c][i];
-          chain_fwd<N1, N2>(net.acts[l], ch, zz, hv);
-#pragma unroll
-          for (int c = 0; c < C; ++c) h[c][i] = hv[c];
-          if (l == TL) {
-            const float wl = fp[FP_WL + j * 8 + i];
-#pragma unroll
-            for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c)
-          store_chunk(cx.P + c * kTileBytes, cx.Q + c * kTileBytes, p, j, h[c], split);
-      }
-    }
-    // ---- last layer (n -> 1, identity): combine the two column halves --------------------------------------------
-    if (hh == 1) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) cx.scratch[c * kTcPts + p] = u[c];
-    }
-    __syncthreads();
-    if (hh == 0) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) u[c] += cx.scratch[c * kTcPts + p];
-      u[0] += fp[FP_BL];
-      for (int t = 0; t < tm.n_taps; ++t)
-        if (tm.tap_slot[t] == slot) {
-          float v = u[0];
-#pragma unroll
-          for (int c = 1; c < C; ++c) v = (tm.tap_ch[t] == c) ? u[c] : v;
-          cx.taps[t * kTcPts + p] = v;
-        }
-    }
-    __syncthreads();
+    // ---- layer 0 on the CUDA cores ------------------------------------------------------------------
+    const int act0 = net.acts[0];
+    const int ng = pi.n1w / 4;
+    LoopCtx lc;
+    lc.fp = fp; lc.bt = fp; lc.tP = tP; lc.tQ = tQ; lc.gb = nullptr; lc.gw = nullptr; lc.taddr = tmem + t.lane_addr;
+    lc.act = act0; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
+    lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
+    l0_fwd_loop<N1, N2, PURE, AK>(&lc, &pi, x, u);
   }
+  // ---- tensor layers -------------------------------------------------------------------------------------
+  for (int l = 1; l <= TL; ++l) {
+    const int n_in = net.dims[l], n_out = net.dims[l + 1];
+    const int act = net.acts[l];
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc::tc_fence_after();
+      if (want_grad) {
+        for (int c = 0; c < C; ++c)
+          tc::bulk_store(stash_slot + (size_t)((l - 1) * kTcMaxC + c) * kTileBytes, tP + c * kTileBytes, kTileBytes);
+        tc::bulk_commit();
+      }
+      const uint32_t idesc = tc::make_idesc(128, n_out, 0, 0);
+      const uint32_t whi = tc::smem_u32(smem + ns.w_hi[l - 1]), wlo = tc::smem_u32(smem + ns.w_lo[l - 1]);
+      const uint64_t dwhi = tc::make_desc(whi, 0, 1024), dwlo = tc::make_desc(wlo, 0, 1024);
+      const int nk = n_in / 16;
+#pragma unroll 1
+      for (int c = 0; c < C; ++c) {
+        const uint64_t dahi = tc::make_desc(tc::smem_u32(tP + c * kTileBytes), 0, 1024);
+        const uint32_t d = tmem + TM_X + c * 64;
+        mma_chain(d, dahi, dwhi, 32, 32, nk, idesc, 0);
+        if (split) {
+          const uint64_t dalo = tc::make_desc(tc::smem_u32(tQ + c * kTileBytes), 0, 1024);
+          mma_chain(d, dahi, dwlo, 32, 32, nk, idesc, 1);
+          mma_chain(d, dalo, dwhi, 32, 32, nk, idesc, 1);
+        }
+      }
+      tc::mma_commit(ms.bar_mma);
+    }
+    wait_bar(ms.bar_mma, mma_phase);
+    tc::tc_fence_after();
+    if (tid == 0 && want_grad) tc::bulk_wait_read0();   // stash copies have finished reading P
+    __syncthreads();
+    const int ng = n_out / 4;
+    LoopCtx lc;
+    lc.fp = fp; lc.bt = fp + FP_BT + (l - 1) * 64; lc.tP = tP; lc.tQ = tQ; lc.gb = nullptr; lc.gw = nullptr;
+    lc.taddr = tmem + t.lane_addr; lc.act = act; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane;
+    lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH); lc.c0 = 0; lc.flag = (l == TL) ? 1 : 0;
+    tl_fwd_loop<N1, N2, PURE, AK>(&lc, &pi, u);
+  }
+  // ---- last layer (n -> 1, identity): combine the column parts of every point ---------------------------------
+  __syncthreads();   // scratch zeroed
+#pragma unroll
+  for (int c = 0; c < C; ++c) atomicAdd(&ms.scratch[c * kTcPts + p], u[c]);
+  __syncthreads();
+  if (hh == 0) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) u[c] = ms.scratch[c * kTcPts + p];
+    u[0] += fp[FP_BL];
+    const int n_taps = tm.n_taps;
+    for (int tt = 0; tt < n_taps; ++tt)
+      if (tm.tap_slot[tt] == slot) {
+        const int tch = tm.tap_ch[tt];
+        float v = u[0];
+#pragma unroll
+        for (int c = 1; c < C; ++c) v = (tch == c) ? u[c] : v;
+        ms.taps[tt * kTcPts + p] = v;
+      }
+  }
+  __syncthreads();
+  return (phase & 2u) | mma_phase;
 }
 
-template <int N1, int N2>
-__device__ __noinline__ void net_backward(TileCtx& cx, const TcArgs& args, const DevProblem& P, const DevTerm& tm, int slot,
-                                          float* partial, uint8_t* stash) {
+// reverse sweep of one network for the current tile
+template <int N1, int N2, bool PURE, int AK>
+__device__ __noinline__ uint32_t net_backward(const CtaShared* cs, const DevProblem* Pp, const DevTerm* tmp, int slot,
+                                              uint32_t phase) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int C = 1 + N1 + N2;
+  const DevTerm& tm = *tmp;
   const int net_id = tm.used_net[slot];
-  const DevNet& net = P.nets[net_id];
+  const DevNet& net = Pp->nets[net_id];
   const DevChan& dc = tm.chan[slot];
-  const TcNetSmem& ns = args.nets[net_id];
-  const float* fp = reinterpret_cast<const float*>(cx.smem + ns.fp);
-  const int L = net.n_layers;
-  const int d_in = net.dims[0];
-  const int TL = L - 2;                         // tensor layers 1..L-2
-  const bool split = args.split != 0;
-  Chan<N1, N2> ch;
-#pragma unroll
-  for (int s = 0; s < N2; ++s) { ch.sa[s] = dc.s_a[s]; ch.sb[s] = dc.s_b[s]; }
-  const int p = cx.p, hh = cx.hh, tid = cx.tid;
+  const TcNetSmem ns = cs->nets[net_id];
+  const float* fp = reinterpret_cast<const float*>(smem + ns.fp);
+  uint8_t* tP = smem + cs->off_P;
+  uint8_t* tQ = smem + cs->off_Q;
+  const Misc ms = misc_of(smem + cs->off_misc);
+  const uint32_t tmem = cs->tmem;
+  float* partial = cs->partial;
+  PassInfo<N1, N2> pi;
+  load_pass<N1, N2>(pi, net, dc);
+  const int L = pi.L, TL = pi.TL;
+  const Tid t = tid_of();
+  const int tid = t.tid, hh = t.hh, p = t.p, lane = t.lane, q = t.q;
+  uint32_t mma_phase = phase & 1u, ld_phase = (phase >> 1) & 1u;
   float x[PINN_MAX_IN];
 #pragma unroll
-  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < d_in) ? cx.Xs[dc.rows[k] * kTcPts + p] : 0.f;
-  uint8_t* stash_slot = stash + (size_t)slot * args.tl_max * kTcMaxC * kTileBytes;
+  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < pi.d_in) ? ms.Xs[dc.rows[k] * kTcPts + p] : 0.f;
+  uint8_t* stash_slot = cs->stash + (size_t)slot * cs->tl_max * kTcMaxC * kTileBytes;
 
-  // =============================== BACKWARD ==============================================================
   // adjoint of the network outputs per channel (every thread of the point needs it)
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = 0.f;
-  for (int t = 0; t < tm.n_taps; ++t)
-    if (tm.tap_slot[t] == slot) {
-      const float g = cx.tapbar[t * kTcPts + p];
-#pragma unroll
-      for (int c = 0; c < C; ++c) ub[c] += (tm.tap_ch[t] == c) ? g : 0.f;
-    }
-  const int nL = net.dims[L - 1];               // width of the last hidden layer
-  // ---- last layer: bias and weight gradient on the CUDA cores -------------------------------------------------------
-  if (hh == 0) {
-    const float s = warp_sum<float>(ub[0]);
-    if (cx.lane == 0) atomicAdd(&partial[net.b_off[L - 1]], s);
-#pragma unroll
-    for (int c = 0; c < C; ++c) cx.scratch[c * kTcPts + p] = ub[c];
-  }
-  __syncthreads();
   {
-    // thread <-> (neuron o = tid & 63, quarter of the points): P still holds H^{L-2}
-    const int o = tid & 63, part = tid >> 6;
-    if (o < nL) {
-      float acc = 0.f;
-      for (int pp = part * 32; pp < part * 32 + 32; ++pp) {
+    const int n_taps = tm.n_taps;
+    for (int tt = 0; tt < n_taps; ++tt)
+      if (tm.tap_slot[tt] == slot) {
+        const float g = ms.tapbar[tt * kTcPts + p];
+        const int tch = tm.tap_ch[tt];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ub[c] += (tch == c) ? g : 0.f;
+      }
+  }
+  // ---- last layer: bias and weight gradient on the CUDA cores -------------------------------------------------------
+  {
+    float* gb_last = partial + net.b_off[L - 1];
+    float* gw_last = partial + net.w_off[L - 1];
+    if (hh == 0) {
+      const float s = warp_sum<float>(ub[0]);
+      if (lane == 0) atomicAdd(gb_last, s);
+#pragma unroll
+      for (int c = 0; c < C; ++c) ms.scratch[c * kTcPts + p] = ub[c];
+    }
+    __syncthreads();
+    // wbar_last[o] = sum_{c,p} ubar_c[p] * H_c^{L-2}[p][o]; P still holds H^{L-2} (bf16 hi).
+    // lane <-> (16-byte chunk j = lane & 7 of 8 neurons, point sub-group lane >> 3); warps stride the points
+    const int j = lane & 7;
+    {
+      const bool jvalid = j * 8 < pi.nL;       // all lanes run the loop and the shuffles; only valid chunks load / add
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int pp = t.warp * 4 + (lane >> 3); pp < kTcPts; pp += (kTcThreads / 32) * 4) {
 #pragma unroll
         for (int c = 0; c < C; ++c) {
-          float hv = load_bf16(cx.P + c * kTileBytes, pp, o);
-          if (split) hv += load_bf16(cx.Q + c * kTileBytes, pp, o);
-          acc = fmaf(cx.scratch[c * kTcPts + pp], hv, acc);
+          uint4 h = make_uint4(0u, 0u, 0u, 0u);
+          if (jvalid) h = *reinterpret_cast<const uint4*>(tP + c * kTileBytes + tc::swz_chunk(pp, j));
+          const float uc = ms.scratch[c * kTcPts + pp];
+          const uint32_t w[4] = {h.x, h.y, h.z, h.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc[2 * i] = fmaf(uc, __uint_as_float(w[i] << 16), acc[2 * i]);
+            acc[2 * i + 1] = fmaf(uc, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
+          }
         }
       }
-      atomicAdd(&partial[net.w_off[L - 1] + o], acc);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (j * 8 + i < pi.nL) atomicAdd(gw_last + j * 8 + i, acc[i]);
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 
   // ---- tensor layers, last to first ------------------------------------------------------------------------------------
   for (int l = TL; l >= 1; --l) {
     const int n_in = net.dims[l], n_out = net.dims[l + 1];
-    const uint32_t whi = tc::smem_u32(cx.smem + ns.w_hi[l - 1]);
+    const int act = net.acts[l];
+    float* gb = partial + net.b_off[l];
+    float* gw = partial + net.w_off[l];
+    const float* bt = fp + FP_BT + (l - 1) * 64;
+    const uint32_t whi = tc::smem_u32(smem + ns.w_hi[l - 1]);
     if (tid == 0) {
       // reload this layer's input tiles H^{l-1} (bf16 hi) from the stash into Q
-      tc::mbar_arrive_expect_tx(cx.bar_ld, C * kTileBytes);
+      tc::mbar_arrive_expect_tx(ms.bar_ld, C * kTileBytes);
       for (int c = 0; c < C; ++c)
-        tc::bulk_load(cx.Q + c * kTileBytes, stash_slot + (size_t)((l - 1) * kTcMaxC + c) * kTileBytes, kTileBytes, cx.bar_ld);
+        tc::bulk_load(tQ + c * kTileBytes, stash_slot + (size_t)((l - 1) * kTcMaxC + c) * kTileBytes, kTileBytes, ms.bar_ld);
     }
-    tc::mbar_wait(cx.bar_ld, cx.ld_phase);
-    cx.ld_phase ^= 1u;
+    wait_bar(ms.bar_ld, ld_phase);
     // recompute pre-activations in groups of <= 32 columns and turn output adjoints into Zbar tiles
-    for (int g0 = 0; g0 < n_out; g0 += 32) {
-      const int gw = (n_out - g0) < 32 ? (n_out - g0) : 32;     // 32 or 16
+    for (int c0 = 0; c0 < n_out; c0 += 32) {
+      const int gw_cols = (n_out - c0) < 32 ? (n_out - c0) : 32;     // 32 or 16
       tc::tc_fence_before();
       __syncthreads();
       if (tid == 0) {
         tc::tc_fence_after();
-        const uint32_t idesc = tc::make_idesc(128, gw, 0, 0);
-        for (int c = 0; c < C; ++c) {
-          const uint32_t a = tc::smem_u32(cx.Q + c * kTileBytes);
-          uint32_t acc = 0;
-          for (int k = 0; k < n_in / 16; ++k) {
-            tc::mma_bf16(cx.tmem + TM_Y + c * 32, tc::make_desc(a + k * 32, 0, 1024),
-                         tc::make_desc(whi + g0 * 128 + k * 32, 0, 1024), idesc, acc);
-            acc = 1;
-          }
-        }
-        tc::mma_commit(cx.bar_mma);
+        const uint32_t idesc = tc::make_idesc(128, gw_cols, 0, 0);
+        const uint64_t dw = tc::make_desc(whi + c0 * 128, 0, 1024);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c)
+          mma_chain(tmem + TM_Y + c * 32, tc::make_desc(tc::smem_u32(tQ + c * kTileBytes), 0, 1024), dw, 32, 32, n_in / 16,
+                    idesc, 0);
+        tc::mma_commit(ms.bar_mma);
       }
-      wait_mma(cx);
-      const int nch = gw / 8, c0 = hh * (nch / 2), c1 = (hh + 1) * (nch / 2);
-      for (int jj = c0; jj < c1; ++jj) {
-        const int ocol = g0 + jj * 8;
-        float z[C][8], hb[C][8], zb[C][8];
-#pragma unroll
-        for (int c = 0; c < C; ++c) tc::tmem_ld8(cx.tmem + cx.lane_addr + TM_Y + c * 32 + jj * 8, z[c]);
-        if (l < TL) {
-#pragma unroll
-          for (int c = 0; c < C; ++c) tc::tmem_ld8(cx.tmem + cx.lane_addr + TM_X + c * 64 + ocol, hb[c]);
-        }
-        tc::tmem_ld_wait();
-        if (l == TL) {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float wl = fp[FP_WL + ocol + i];
-#pragma unroll
-            for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float zz[C], hv[C], zv[C];
-          zz[0] = z[0][i] + fp[FP_BT + (l - 1) * 64 + ocol + i];
-#pragma unroll
-          for (int c = 1; c < C; ++c) zz[c] = z[c][i];
-#pragma unroll
-          for (int c = 0; c < C; ++c) hv[c] = hb[c][i];
-          chain_bwd<N1, N2>(net.acts[l], ch, zz, hv, zv);
-#pragma unroll
-          for (int c = 0; c < C; ++c) zb[c][i] = zv[c];
-          const float bs = warp_sum<float>(zv[0]);
-          if (cx.lane == 0) atomicAdd(&partial[net.b_off[l] + ocol + i], bs);
-        }
-#pragma unroll
-        for (int c = 0; c < C; ++c) store_chunk(cx.P + c * kTileBytes, cx.P, p, ocol >> 3, zb[c], false);
-      }
+      wait_bar(ms.bar_mma, mma_phase);
+      tc::tc_fence_after();
+      const int ng = gw_cols / 4;
+      LoopCtx lc;
+      lc.fp = fp; lc.bt = bt; lc.tP = tP; lc.tQ = tQ; lc.gb = gb; lc.gw = nullptr; lc.taddr = tmem + t.lane_addr;
+      lc.act = act; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
+      lc.c0 = c0; lc.flag = (l == TL) ? 1 : 0;
+      tl_bwd_loop<N1, N2, PURE, AK>(&lc, &pi, ub);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
@@ -428,39 +698,33 @@ __device__ __noinline__ void net_backward(TileCtx& cx, const TcArgs& args, const
       tc::tc_fence_after();
       // dgrad: Hbar_c = Zbar_c * W_l  -> X
       const uint32_t idg = tc::make_idesc(128, n_in, 0, 1);
-      for (int c = 0; c < C; ++c) {
-        const uint32_t a = tc::smem_u32(cx.P + c * kTileBytes);
-        uint32_t acc = 0;
-        for (int k = 0; k < n_out / 16; ++k) {
-          tc::mma_bf16(cx.tmem + TM_X + c * 64, tc::make_desc(a + k * 32, 0, 1024),
-                       tc::make_desc(whi + k * 2048, 0, 1024), idg, acc);
-          acc = 1;
-        }
-      }
+      const uint64_t dw = tc::make_desc(whi, 0, 1024);
+#pragma unroll 1
+      for (int c = 0; c < C; ++c)
+        mma_chain(tmem + TM_X + c * 64, tc::make_desc(tc::smem_u32(tP + c * kTileBytes), 0, 1024), dw, 32, 2048, n_out / 16,
+                  idg, 0);
       // wgrad: Wbar_l = sum_c Zbar_c^T * H_c -> Y (rows >= 64 alias rows - 64 through LBO = 0)
       const uint32_t iwg = tc::make_idesc(128, n_in, 1, 1);
-      uint32_t acc = 0;
-      for (int c = 0; c < C; ++c) {
-        const uint32_t a = tc::smem_u32(cx.P + c * kTileBytes), b = tc::smem_u32(cx.Q + c * kTileBytes);
-        for (int k = 0; k < kTcPts / 16; ++k) {
-          tc::mma_bf16(cx.tmem + TM_Y, tc::make_desc(a + k * 2048, 0, 1024), tc::make_desc(b + k * 2048, 0, 1024), iwg, acc);
-          acc = 1;
-        }
-      }
-      tc::mma_commit(cx.bar_mma);
+#pragma unroll 1
+      for (int c = 0; c < C; ++c)
+        mma_chain(tmem + TM_Y, tc::make_desc(tc::smem_u32(tP + c * kTileBytes), 0, 1024),
+                  tc::make_desc(tc::smem_u32(tQ + c * kTileBytes), 0, 1024), 2048, 2048, kTcPts / 16, iwg, c > 0 ? 1u : 0u);
+      tc::mma_commit(ms.bar_mma);
     }
-    wait_mma(cx);
+    wait_bar(ms.bar_mma, mma_phase);
+    tc::tc_fence_after();
     // flush the weight-gradient tile: TMEM lane = output neuron o, column = input neuron k
-    if (cx.q < 2) {
-      const int o = cx.q * 32 + cx.lane;
-      const int half = n_in / 2;
-      for (int k0 = hh * half; k0 < (hh + 1) * half; k0 += 8) {
-        float v[8];
-        tc::tmem_ld8(cx.tmem + cx.lane_addr + TM_Y + k0, v);
+    if (q < 2) {
+      const int o = q * 32 + lane;
+      const int part = n_in / kNH;
+#pragma unroll 1
+      for (int k0 = hh * part; k0 < (hh + 1) * part; k0 += 4) {
+        float v[4];
+        tmem_ld4(tmem + t.lane_addr + TM_Y + k0, v);
         tc::tmem_ld_wait();
         if (o < n_out) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) partial[net.w_off[l] + o + (long long)n_out * (k0 + i)] += v[i];
+          for (int i = 0; i < 4; ++i) atomicAdd(gw + o + (long long)n_out * (k0 + i), v[i]);
         }
       }
     }
@@ -471,105 +735,83 @@ __device__ __noinline__ void net_backward(TileCtx& cx, const TcArgs& args, const
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
-    const int n1w = net.dims[1];
-    const int nch = n1w / 8, c0 = hh * (nch / 2), c1 = (hh + 1) * (nch / 2);
-    for (int j = c0; j < c1; ++j) {
-      float z[C][8], hb[C][8];
-      first_layer_z<N1, N2>(fp, dc, x, d_in, j * 8, z);
-      if (TL > 0) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) tc::tmem_ld8(cx.tmem + cx.lane_addr + TM_X + c * 64 + j * 8, hb[c]);
-        tc::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float wl = fp[FP_WL + j * 8 + i];
-#pragma unroll
-          for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int o = j * 8 + i;
-        float zz[C], hv[C], zv[C];
-#pragma unroll
-        for (int c = 0; c < C; ++c) { zz[c] = z[c][i]; hv[c] = hb[c][i]; }
-        chain_bwd<N1, N2>(net.acts[0], ch, zz, hv, zv);
-        // Wbar_0[o][k] = sum_p zbar_0 x_k + zbar_(channel of direction k);  bbar_0[o] = sum_p zbar_0
-        const float bs = warp_sum<float>(zv[0]);
-        if (cx.lane == 0) atomicAdd(&partial[net.b_off[0] + o], bs);
-#pragma unroll
-        for (int k = 0; k < PINN_MAX_IN; ++k) {
-          if (k < d_in) {
-            float g = zv[0] * x[k];
-#pragma unroll
-            for (int jd = 0; jd < N1; ++jd) g += (dc.dir1[jd] == k) ? zv[1 + jd] : 0.f;
-            g = warp_sum<float>(g);
-            if (cx.lane == 0) atomicAdd(&partial[net.w_off[0] + o + (long long)n1w * k], g);
-          }
-        }
-      }
-    }
+    const int act0 = net.acts[0];
+    float* gb0 = partial + net.b_off[0];
+    float* gw0 = partial + net.w_off[0];
+    const int ng = pi.n1w / 4;
+    LoopCtx lc;
+    lc.fp = fp; lc.bt = fp; lc.tP = tP; lc.tQ = tQ; lc.gb = gb0; lc.gw = gw0; lc.taddr = tmem + t.lane_addr;
+    lc.act = act0; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
+    lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
+    l0_bwd_loop<N1, N2, PURE, AK>(&lc, &pi, x, ub);
   }
   __syncthreads();
+  return (ld_phase << 1) | mma_phase;
 }
 
-#define PINN_TC_DISPATCH(n1, n2, CALL)                                        \
+#define PINN_TC_CASE(a1, a2, pu, CALL)                                                    \
+  {                                                                                       \
+    constexpr int A1 = a1, A2 = a2;                                                       \
+    constexpr bool PU = pu;                                                               \
+    if (_ak == 1) { constexpr int AK = 1; CALL; } else { constexpr int AK = 0; CALL; }   \
+  }                                                                                       \
+  break
+// ak = 1 when every hidden layer of the network is tanh (fast branch-free activation), else 0
+#define PINN_TC_DISPATCH(n1, n2, pure, ak, CALL)                              \
   do {                                                                        \
-    const int _key = (n1) * 8 + (n2);                                         \
+    const int _ak = (ak);                                                     \
+    const int _key = ((n1) * 8 + (n2)) * 2 + ((pure) ? 1 : 0);                \
     switch (_key) {                                                           \
-      case 0 * 8 + 0: { constexpr int A1 = 0, A2 = 0; CALL; } break;          \
-      case 1 * 8 + 0: { constexpr int A1 = 1, A2 = 0; CALL; } break;          \
-      case 2 * 8 + 0: { constexpr int A1 = 2, A2 = 0; CALL; } break;          \
-      case 3 * 8 + 0: { constexpr int A1 = 3, A2 = 0; CALL; } break;          \
-      case 4 * 8 + 0: { constexpr int A1 = 4, A2 = 0; CALL; } break;          \
-      case 1 * 8 + 1: { constexpr int A1 = 1, A2 = 1; CALL; } break;          \
-      case 2 * 8 + 1: { constexpr int A1 = 2, A2 = 1; CALL; } break;          \
-      case 3 * 8 + 1: { constexpr int A1 = 3, A2 = 1; CALL; } break;          \
-      case 2 * 8 + 2: { constexpr int A1 = 2, A2 = 2; CALL; } break;          \
+      case (0 * 8 + 0) * 2: case (0 * 8 + 0) * 2 + 1: PINN_TC_CASE(0, 0, true, CALL);   \
+      case (1 * 8 + 0) * 2: case (1 * 8 + 0) * 2 + 1: PINN_TC_CASE(1, 0, true, CALL);   \
+      case (2 * 8 + 0) * 2: case (2 * 8 + 0) * 2 + 1: PINN_TC_CASE(2, 0, true, CALL);   \
+      case (3 * 8 + 0) * 2: case (3 * 8 + 0) * 2 + 1: PINN_TC_CASE(3, 0, true, CALL);   \
+      case (4 * 8 + 0) * 2: case (4 * 8 + 0) * 2 + 1: PINN_TC_CASE(4, 0, true, CALL);   \
+      case (1 * 8 + 1) * 2: case (1 * 8 + 1) * 2 + 1: PINN_TC_CASE(1, 1, true, CALL);   \
+      case (2 * 8 + 1) * 2 + 1: PINN_TC_CASE(2, 1, true, CALL);               \
+      case (2 * 8 + 1) * 2: PINN_TC_CASE(2, 1, false, CALL);                  \
+      case (3 * 8 + 1) * 2 + 1: PINN_TC_CASE(3, 1, true, CALL);               \
+      case (3 * 8 + 1) * 2: PINN_TC_CASE(3, 1, false, CALL);                  \
+      case (2 * 8 + 2) * 2 + 1: PINN_TC_CASE(2, 2, true, CALL);               \
+      case (2 * 8 + 2) * 2: PINN_TC_CASE(2, 2, false, CALL);                  \
       default: break;                                                         \
     }                                                                         \
   } while (0)
 
-__global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const TcArgs args) {
+__global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __grid_constant__ TcArgs args) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int tid = threadIdx.x;
-  const DevProblem& P = *args.prob;
-  TileCtx cx;
-  cx.smem = smem;
-  cx.P = smem + args.off_P;
-  cx.Q = smem + args.off_Q;
-  uint8_t* misc = smem + args.off_misc;
-  cx.Xs = reinterpret_cast<float*>(misc);             misc += PINN_MAX_DIM * kTcPts * 4;
-  cx.taps = reinterpret_cast<float*>(misc);           misc += kTcMaxTaps * kTcPts * 4;
-  cx.tapbar = reinterpret_cast<float*>(misc);         misc += kTcMaxTaps * kTcPts * 4;
-  cx.scratch = reinterpret_cast<float*>(misc);        misc += kTcMaxC * kTcPts * 4;
-  cx.qws = reinterpret_cast<float*>(misc);            misc += kTcPts * 4;
-  cx.rres = reinterpret_cast<float*>(misc);           misc += kTcPts * 4;
-  cx.tsum = reinterpret_cast<double*>(misc);          misc += PINN_MAX_TERMS * 8;
-  cx.bar_mma = reinterpret_cast<uint64_t*>(misc);     misc += 8;
-  cx.bar_ld = reinterpret_cast<uint64_t*>(misc);      misc += 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc);
-  cx.tid = tid; cx.warp = tid >> 5; cx.lane = tid & 31; cx.q = cx.warp & 3; cx.hh = cx.warp >> 2;
-  cx.p = cx.q * 32 + cx.lane;
-  cx.lane_addr = (uint32_t)(cx.q * 32) << 16;
-  cx.mma_phase = 0; cx.ld_phase = 0;
-
+  __shared__ CtaShared cs;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const DevProblem* Pp = args.prob;
+  const DevProblem& P = *Pp;
+  const Misc ms = misc_of(smem + args.off_misc);
   float* partial = args.partial + (long long)blockIdx.x * P.n_theta;
-  uint8_t* stash = args.stash + (long long)blockIdx.x * args.stash_per_cta;
   const bool want_grad = (args.mode == 0);
   const float* theta = args.theta;
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------------------------
   if (tid == 0) {
-    tc::mbar_init(cx.bar_mma, 1);
-    tc::mbar_init(cx.bar_ld, 1);
+    tc::mbar_init(ms.bar_mma, 1);
+    tc::mbar_init(ms.bar_ld, 1);
     tc::fence_barrier_init();
+    cs.split = args.split; cs.tl_max = args.tl_max; cs.off_P = args.off_P; cs.off_Q = args.off_Q;
+    cs.off_misc = args.off_misc; cs.partial = partial;
+    cs.stash = args.stash + (long long)blockIdx.x * args.stash_per_cta;
+    cs.theta = theta;
+    for (int k = 0; k < PINN_MAX_NETS; ++k) cs.nets[k] = args.nets[k];
   }
-  if (cx.warp == 0) tc::tmem_alloc<512>(tmem_slot);
-  if (want_grad)
-    for (long long i = tid; i < P.n_theta; i += kTcThreads) partial[i] = 0.f;
-  if (tid < PINN_MAX_TERMS) cx.tsum[tid] = 0.0;
+  if (warp == 0) tc::tmem_alloc<512>(ms.tmem_slot);
+  if (want_grad) {
+    const long long n4 = P.n_theta / 4;
+    float4* p4 = reinterpret_cast<float4*>(partial);
+    if ((reinterpret_cast<uintptr_t>(partial) & 15) == 0) {
+      for (long long i = tid; i < n4; i += kTcThreads) p4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long i = n4 * 4 + tid; i < P.n_theta; i += kTcThreads) partial[i] = 0.f;
+    } else {
+      for (long long i = tid; i < P.n_theta; i += kTcThreads) partial[i] = 0.f;
+    }
+  }
+  if (tid < PINN_MAX_TERMS) ms.tsum[tid] = 0.0;
   // stage weights: bf16 hi / lo operand tiles of the tensor layers, fp32 blocks of the first / last layers
   for (int kn = 0; kn < P.n_nets; ++kn) {
     const DevNet& net = P.nets[kn];
@@ -580,60 +822,82 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const TcArg
     for (int i = tid; i < FP_SIZE; i += kTcThreads) fp[i] = 0.f;
     __syncthreads();
     const int n1w = net.dims[1], d_in = net.dims[0];
+    const long long w0 = net.w_off[0], b0 = net.b_off[0];
     for (int i = tid; i < n1w * d_in; i += kTcThreads) {
       const int o = i % n1w, k = i / n1w;
-      fp[FP_W1 + o * 8 + k] = __ldg(&theta[net.w_off[0] + i]);
+      fp[FP_W1 + o * 8 + k] = __ldg(&theta[w0 + i]);
     }
-    for (int i = tid; i < n1w; i += kTcThreads) fp[FP_B1 + i] = __ldg(&theta[net.b_off[0] + i]);
+    for (int i = tid; i < n1w; i += kTcThreads) fp[FP_B1 + i] = __ldg(&theta[b0 + i]);
     for (int l = 1; l <= L - 2; ++l) {
       const int n_in = net.dims[l], n_out = net.dims[l + 1];
+      const long long woff = net.w_off[l], boff = net.b_off[l];
       uint8_t* thi = smem + ns.w_hi[l - 1];
       uint8_t* tlo = smem + ns.w_lo[l - 1];
-      for (int i = tid; i < 64 * 64; i += kTcThreads) {
-        const int o = i & 63, k = i >> 6;
-        float w = (o < n_out && k < n_in) ? __ldg(&theta[net.w_off[l] + o + (long long)n_out * k]) : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(w);
-        *reinterpret_cast<__nv_bfloat16*>(thi + tc::swz_off(o, k)) = h;
-        if (args.split) *reinterpret_cast<__nv_bfloat16*>(tlo + tc::swz_off(o, k)) = __float2bfloat16_rn(w - __bfloat162float(h));
+      // thread <-> (row o, chunk of 8 k): coalesced-ish reads along o, one 16-byte swizzled store
+      for (int i = tid; i < 64 * 8; i += kTcThreads) {
+        const int o = i & 63, kc = i >> 6;
+        float w[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = kc * 8 + e;
+          w[e] = (o < n_out && k < n_in) ? __ldg(&theta[woff + o + (long long)n_out * k]) : 0.f;
+        }
+        uint4 h, lo4;
+        h.x = tc::pack_bf16(w[0], w[1]); h.y = tc::pack_bf16(w[2], w[3]);
+        h.z = tc::pack_bf16(w[4], w[5]); h.w = tc::pack_bf16(w[6], w[7]);
+        *reinterpret_cast<uint4*>(thi + tc::swz_chunk(o, kc)) = h;
+        if (args.split) {
+          lo4.x = tc::pack_bf16(w[0] - __uint_as_float(h.x << 16), w[1] - __uint_as_float(h.x & 0xffff0000u));
+          lo4.y = tc::pack_bf16(w[2] - __uint_as_float(h.y << 16), w[3] - __uint_as_float(h.y & 0xffff0000u));
+          lo4.z = tc::pack_bf16(w[4] - __uint_as_float(h.z << 16), w[5] - __uint_as_float(h.z & 0xffff0000u));
+          lo4.w = tc::pack_bf16(w[6] - __uint_as_float(h.w << 16), w[7] - __uint_as_float(h.w & 0xffff0000u));
+          *reinterpret_cast<uint4*>(tlo + tc::swz_chunk(o, kc)) = lo4;
+        }
       }
-      for (int i = tid; i < n_out; i += kTcThreads) fp[FP_BT + (l - 1) * 64 + i] = __ldg(&theta[net.b_off[l] + i]);
+      for (int i = tid; i < n_out; i += kTcThreads) fp[FP_BT + (l - 1) * 64 + i] = __ldg(&theta[boff + i]);
     }
     const int nL = net.dims[L - 1];
-    for (int i = tid; i < nL; i += kTcThreads) fp[FP_WL + i] = __ldg(&theta[net.w_off[L - 1] + i]);
-    if (tid == 0) fp[FP_BL] = __ldg(&theta[net.b_off[L - 1]]);
+    const long long wl = net.w_off[L - 1], bl = net.b_off[L - 1];
+    for (int i = tid; i < nL; i += kTcThreads) fp[FP_WL + i] = __ldg(&theta[wl + i]);
+    if (tid == 0) fp[FP_BL] = __ldg(&theta[bl]);
   }
   tc::fence_async_smem();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  cx.tmem = *tmem_slot;
+  if (tid == 0) cs.tmem = *ms.tmem_slot;
+  __syncthreads();
+  uint32_t phase = 0;
 
   for (int tile = args.tile_begin + blockIdx.x; tile < args.tile_end; tile += gridDim.x) {
     int ti = 0;
     while (ti + 1 < P.n_terms && tile >= args.dyn[ti + 1].tile0) ++ti;
-    const DevTerm& tm = P.terms[ti];
+    const DevTerm* tmp = &P.terms[ti];
+    const DevTerm& tm = *tmp;
     const long long p0 = (long long)(tile - args.dyn[ti].tile0) * kTcPts;
     const long long n_pts = args.dyn[ti].n;
     const float* pts = reinterpret_cast<const float*>(args.dyn[ti].pts);
     const float* qw = reinterpret_cast<const float*>(args.dyn[ti].qw);
-    for (int i = tid; i < tm.dim * kTcPts; i += kTcThreads) {
-      int pp = i / tm.dim, r = i - pp * tm.dim;
+    const int dim = tm.dim, n_taps = tm.n_taps, n_used = tm.n_used, weighted = tm.weighted;
+    for (int i = tid; i < dim * kTcPts; i += kTcThreads) {
+      int pp = i / dim, r = i - pp * dim;
       long long gp = p0 + pp;
       if (gp >= n_pts) gp = n_pts - 1;
-      cx.Xs[r * kTcPts + pp] = pts[gp * tm.dim + r];
+      ms.Xs[r * kTcPts + pp] = pts[gp * dim + r];
     }
     if (tid < kTcPts) {
       long long gp = p0 + tid;
       float w = 0.f;
-      if (gp < n_pts) w = tm.weighted ? qw[gp] : 1.f;
-      cx.qws[tid] = w;
+      if (gp < n_pts) w = weighted ? qw[gp] : 1.f;
+      ms.qws[tid] = w;
     }
-    for (int i = tid; i < tm.n_taps * kTcPts; i += kTcThreads) cx.tapbar[i] = 0.f;
+    for (int i = tid; i < n_taps * kTcPts; i += kTcThreads) ms.tapbar[i] = 0.f;
     __syncthreads();
 
-    for (int slot = 0; slot < tm.n_used; ++slot) {
-      const DevChan& dc = tm.chan[slot];
-      PINN_TC_DISPATCH(dc.n1, dc.n2, (net_forward<A1, A2>(cx, args, P, tm, slot, want_grad, stash)));
+    for (int slot = 0; slot < n_used; ++slot) {
+      const int k1 = tm.chan[slot].n1, k2 = tm.chan[slot].n2, pu = tm.chan[slot].pure;
+      const int ak = args.net_ak[tm.used_net[slot]];
+      PINN_TC_DISPATCH(k1, k2, pu, ak, (phase = net_forward<A1, A2, PU, AK>(&cs, Pp, tmp, slot, want_grad ? 1 : 0, phase)));
     }
 
     // ---- residual program, loss partial, tap adjoints (threads 0..127: one point each) -----------------------------------------
@@ -641,22 +905,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const TcArg
       float pbar[PINN_MAX_PARAMS];
 #pragma unroll
       for (int j = 0; j < PINN_MAX_PARAMS; ++j) pbar[j] = 0.f;
-      const float r = run_program<float, kTcPts>(tm, theta + P.param_off, cx.Xs, cx.taps, cx.tapbar, pbar, tid, want_grad);
-      const float w = cx.qws[tid];
+      const float r = run_program<float, kTcPts>(tm, theta + P.param_off, ms.Xs, ms.taps, ms.tapbar, pbar, tid, want_grad);
+      const float w = ms.qws[tid];
       double s = (double)w * (double)r * (double)r;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (cx.lane == 0) atomicAdd(&cx.tsum[ti], s);
+      if (lane == 0) atomicAdd(&ms.tsum[ti], s);
       if (args.mode == 2) {
         long long gp = p0 + tid;
         if (gp < n_pts) args.resid_out[gp] = r;
       }
       if (want_grad) {
         const float g = (float)args.seed[ti] * w * 2.f * r;
-        for (int t = 0; t < tm.n_taps; ++t) cx.tapbar[t * kTcPts + tid] *= g;
-        for (int j = 0; j < P.n_params; ++j) {
+        for (int tt = 0; tt < n_taps; ++tt) ms.tapbar[tt * kTcPts + tid] *= g;
+        const int n_params = P.n_params;
+        for (int j = 0; j < n_params; ++j) {
           float v = warp_sum<float>(pbar[j] * g);
-          if (cx.lane == 0) atomicAdd(&partial[P.param_off + j], v);
+          if (lane == 0) atomicAdd(&partial[P.param_off + j], v);
         }
       }
     }
@@ -665,21 +930,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const TcArg
     if (want_grad) {
       if (tid == 0) tc::bulk_wait0();             // stash writes of this tile are complete before reloads
       __syncthreads();
-      for (int slot = tm.n_used - 1; slot >= 0; --slot) {
-        const DevChan& dc = tm.chan[slot];
-        if (tm.n_used > 1) {
+      for (int slot = n_used - 1; slot >= 0; --slot) {
+        const int k1 = tm.chan[slot].n1, k2 = tm.chan[slot].n2, pu = tm.chan[slot].pure;
+        const int ak = args.net_ak[tm.used_net[slot]];
+        if (n_used > 1) {
           // P must hold this slot's last hidden activations again: recompute its forward
-          PINN_TC_DISPATCH(dc.n1, dc.n2, (net_forward<A1, A2>(cx, args, P, tm, slot, false, stash)));
+          PINN_TC_DISPATCH(k1, k2, pu, ak, (phase = net_forward<A1, A2, PU, AK>(&cs, Pp, tmp, slot, 0, phase)));
         }
-        PINN_TC_DISPATCH(dc.n1, dc.n2, (net_backward<A1, A2>(cx, args, P, tm, slot, partial, stash)));
+        PINN_TC_DISPATCH(k1, k2, pu, ak, (phase = net_backward<A1, A2, PU, AK>(&cs, Pp, tmp, slot, phase)));
       }
     }
   }
 
   tc::tc_fence_before();
   __syncthreads();
-  if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = cx.tsum[tid];
-  if (cx.warp == 0) tc::tmem_dealloc<512>(cx.tmem);
+  if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = ms.tsum[tid];
+  if (warp == 0) tc::tmem_dealloc<512>(cs.tmem);
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------

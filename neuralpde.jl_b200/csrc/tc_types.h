@@ -43,6 +43,7 @@ struct TcArgs {
   float* resid_out;
   int off_P, off_Q, off_misc;   // byte offsets into dynamic shared memory
   TcNetSmem nets[PINN_MAX_NETS];
+  int net_ak[PINN_MAX_NETS];   // 1: every hidden activation is tanh (fast path), 0: generic
   double seed[PINN_MAX_TERMS];
   TermDyn dyn[PINN_MAX_TERMS];
 };
