@@ -42,25 +42,48 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clock, power and throttle reasons during the timed region (NVML, ~2 ms period;
+    falls back to nvidia-smi)."""
 
     def __init__(self, index: int):
         self.index, self.rows, self._stop, self._t = index, [], threading.Event(), None
 
-    def _run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    def _run_nvml(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+        while not self._stop.is_set():
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((float(clk), float(mx), {k for k, b in bits.items() if rs & b}))
+            except Exception:
+                pass
+            self._stop.wait(0.002)
+
+    def _run_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         while not self._stop.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [s.strip() for s in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.rows.append(parts)
+                p = [s.strip() for s in out.strip().split(",")]
+                if len(p) >= 6:
+                    self.rows.append((float(p[0]), float(p[1]), {n for n, v in zip(names, p[2:6]) if v.lower().startswith("active")}))
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.05)
+
+    def _run(self):
+        try:
+            self._run_nvml()
+        except Exception:
+            self._run_smi()
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -70,14 +93,11 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        sm = [r[0] for r in self.rows]
         reasons = set()
         for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            reasons |= r[2]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None,
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
@@ -96,7 +116,7 @@ def cpu_reference_eval(cfg, theta64, sets, threads: int, reps: int):
     import torch
     from oracle import reference as R
     torch.set_num_threads(threads)
-    prob = R.Problem(cfg.pde_system, cfg.oracle_chains(), param_estim=cfg.param_estim, derivative="fd")
+    prob = R.Problem(cfg.pde_system, cfg.chain_specs(), param_estim=cfg.param_estim, derivative="fd")
     n_pde = len(cfg.pde_system.eqs)
     ps, bs = sets[:n_pde], sets[n_pde:]
     times, L = [], None
@@ -105,6 +125,19 @@ def cpu_reference_eval(cfg, theta64, sets, threads: int, reps: int):
         L, _, _ = prob.loss_and_grad(theta64, ps, bs)
         times.append(time.perf_counter() - t0)
     return L, times
+
+
+def best_thread_count(cfg, theta64, sets, cores: int) -> int:
+    """The reference side gets the thread count that serves it best (oversubscribing small GEMMs on a
+    many-core host is slower than using fewer threads)."""
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    best, best_t = cands[0], float("inf")
+    for c in cands:
+        cpu_reference_eval(cfg, theta64, sets, c, 1)
+        _, t = cpu_reference_eval(cfg, theta64, sets, c, 2)
+        if min(t) < best_t:
+            best, best_t = c, min(t)
+    return best
 
 
 def run_reference(args, rank: int, world: int):
@@ -116,10 +149,9 @@ def run_reference(args, rank: int, world: int):
     sys_ = cfg.pde_system
     ps, bs = R.generate_training_sets(sys_.domain, cfg.strategy.dx, sys_.eqs, sys_.bcs, sys_.ivs, sys_.dvs)
     n_pts = sum(p.shape[1] for p in ps)
-    cores = os.cpu_count() or 1
     theta = cfg.init_params(np.float64)
+    cores = best_thread_count(cfg, theta, ps + bs, os.cpu_count() or 1)
     _, tw = cpu_reference_eval(cfg, theta, ps + bs, cores, 1)          # warm-up, also sizes the sample
-    _, tw = cpu_reference_eval(cfg, theta, ps + bs, cores, 1)
     budget = 150.0                                                     # seconds for the K timed steps
     frac = min(1.0, budget / max(args.steps * tw[0], 1e-9))
     if frac < 1.0:                                                     # bounded sample: leading fraction of every set
@@ -259,20 +291,44 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk_kind,
                          "kernel": "ffma_loss_grad_kernel" if args.mode == "ffma" else "tc_loss_grad_kernel",
+                         "arithmetic": {"ffma": "fp32 FMA on CUDA cores", "tc_bf16": "tcgen05 bf16 x bf16 -> fp32",
+                                        "tc_split": "tcgen05 split-bf16 (3 MMAs per product in the forward sweep)"}[args.mode],
                          "kernel_ms": kernel_ms, "flops_per_launch": flops,
                          "note": "algorithmic FLOPs 6*C*S per point (SURVEY 8(d)) / fused-kernel duration"},
         }
+        if world == 1 and not args.no_alt_modes:
+            # the other arithmetic modes on the same workload (device-resident, kernel + reduction), for context
+            alt = {}
+            for m in ("ffma", "tc_bf16", "tc_split"):
+                if m == args.mode:
+                    continue
+                d2 = cfg.discretization(dtype=dtype, mode=m, device=local_rank)
+                r2 = npde.symbolic_discretize(cfg.pde_system, d2)
+                for _ in range(3):
+                    r2.engine.loss_grad_device(theta_d, grad_d, terms_d, total_d, None, stream)
+                e2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for a, b in e2:
+                    flush.zero_()
+                    a.record()
+                    r2.engine.loss_grad_device(theta_d, grad_d, terms_d, total_d, None, stream)
+                    b.record()
+                torch.cuda.synchronize()
+                ms2 = float(np.mean([a.elapsed_time(b) for a, b in e2]))
+                alt[m] = {"ms_per_step": ms2, "value": n_pts_global / (ms2 * 1e-3), "loss": float(total_d.item())}
+                r2.engine.close()
+            line["config"]["other_modes"] = alt
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
             sets = rep.point_sets[:n_pde + len(cfg.pde_system.bcs)]
+            cores = best_thread_count(cfg, theta_h.astype(np.float64), sets, os.cpu_count() or 1)
             reps = 5
             cpu_reference_eval(cfg, theta_h.astype(np.float64), sets, cores, 1)
             Lc, times = cpu_reference_eval(cfg, theta_h.astype(np.float64), sets, cores, reps)
             line["cpu_baseline"] = {
                 "value": n_pts_global / float(np.median(times)), "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": "%d full loss+grad evaluations of the same workload (median); CPU restatement of the "
-                          "reference algorithm (FD stencils, PyTorch-CPU float64), not Julia" % reps,
-                "loss": Lc, "loss_rel_err_engine": abs(loss_val - Lc) / abs(Lc)}
+                          "reference algorithm (FD stencils, PyTorch-CPU float64, best of 8/16/32/64/all threads), not "
+                          "Julia" % reps,
+                "host_cores": os.cpu_count(), "loss": Lc, "loss_rel_err_engine": abs(loss_val - Lc) / abs(Lc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -285,9 +341,10 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("PINN_BENCH_MODE", "ffma"), choices=["ffma", "tc_bf16", "tc_split"])
+    ap.add_argument("--mode", default=os.environ.get("PINN_BENCH_MODE", "tc_split"), choices=["ffma", "tc_bf16", "tc_split"])
     ap.add_argument("--n", type=int, default=128, help="grid points per axis (128 = BASELINE configs[1])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt-modes", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

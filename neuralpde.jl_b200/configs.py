@@ -44,7 +44,7 @@ class Config:
                                  param_estim=self.param_estim, additional_loss=self.additional_loss, mode=mode,
                                  device=device, **kw)
 
-    def oracle_chains(self):
+    def chain_specs(self):
         return [(c.dims, c.acts) for c in self.chains]
 
 

@@ -16,11 +16,25 @@ template <typename real>
 __global__ void reduce_kernel(const real* __restrict__ partial, const double* __restrict__ term_sums, int nb,
                               long long n_theta, int n_terms, const ScaleW sw,
                               real* out_grad, real* out_terms, real* out_total, int want_grad) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (want_grad && i < n_theta) {
+  // block = 32 gradient entries x 8 slices of the CTA partials; fixed summation order (slice-major)
+  __shared__ real red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + tx;
+  if (want_grad) {
     real s = real(0);
-    for (int b = 0; b < nb; ++b) s += partial[(long long)b * n_theta + i];
-    out_grad[i] = s;
+    if (i < n_theta) {
+      const int chunk = (nb + 7) / 8;
+      const int b0 = ty * chunk, b1 = (b0 + chunk < nb) ? b0 + chunk : nb;
+      for (int b = b0; b < b1; ++b) s += partial[(long long)b * n_theta + i];
+    }
+    red[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && i < n_theta) {
+      real t = red[0][tx];
+#pragma unroll
+      for (int k = 1; k < 8; ++k) t += red[k][tx];
+      out_grad[i] = t;
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x < 32) {
     double tot = 0.0;
@@ -78,7 +92,7 @@ cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sum
                           int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
                           int want_grad, cudaStream_t st) {
   long long n = want_grad ? n_theta : 1;
-  int blocks = (int)((n + 255) / 256);
+  int blocks = (int)((n + 31) / 32);
   if (blocks < 1) blocks = 1;
   if (dtype == PINN_F64)
     reduce_kernel<double><<<blocks, 256, 0, st>>>((const double*)partial, term_sums, nb, n_theta, n_terms, scale_w,

@@ -1,0 +1,75 @@
+"""Parity cases shared by the golden generator, the CPU tests and the GPU tests."""
+import numpy as np
+import sympy as sp
+
+import neuralpde_jl_b200 as npde
+from neuralpde_jl_b200 import configs
+from neuralpde_jl_b200.configs import Config, mlp
+from neuralpde_jl_b200.pinn import Chain, Dense
+from neuralpde_jl_b200.strategies import (GridTraining, QuadratureTraining, QuasiRandomTraining, StochasticTraining,
+                                          gauss_legendre_box, generate_quasi_random_points, generate_random_points,
+                                          generate_training_sets, get_bounds)
+from neuralpde_jl_b200.symbolic import Differential, Eq, In, PDESystem, get_vars, parameters, variables
+
+
+def mixed_derivative_case() -> Config:
+    """u_xx + u_xy - 2 u_yy = -1 style equation (reference test/NNPDE1/nnpde__pde_vi_pde_with_mixed_derivative.jl)."""
+    x, y = parameters("x y")
+    u = variables("u")
+    Dx, Dy = Differential(x), Differential(y)
+    Dxx, Dyy = Dx ** 2, Dy ** 2
+    eq = Eq(Dxx(u(x, y)) + Dx(Dy(u(x, y))) - 2 * Dyy(u(x, y)), -1.0)
+    bcs = [Eq(u(x, 0), x), Eq(Dy(u(x, 0)), x), Eq(u(0, y), sp.exp(y) - 1), Eq(u(1, y), sp.exp(y))]
+    sys_ = PDESystem(eq, bcs, [In(x, 0.0, 1.0), In(y, 0.0, 1.0)], [x, y], [u(x, y)])
+    return Config("mixed_derivative", sys_, [mlp(2, 16, 2, "sigmoid")], GridTraining(0.1), n_pde_points=121)
+
+
+def neumann_sin_case() -> Config:
+    """1-D problem with a Neumann bc and sin / softplus activations (value + first-derivative channels)."""
+    x = parameters("x")
+    u = variables("u")
+    Dx = Differential(x)
+    eq = Eq((Dx ** 2)(u(x)) + u(x) * Dx(u(x)), sp.cos(2 * x) * sp.exp(-x) + x ** 3 / (1 + x ** 2))
+    bcs = [Eq(u(0.0), 0.5), Eq(Dx(u(1.0)), -0.25)]
+    sys_ = PDESystem(eq, bcs, [In(x, 0.0, 1.0)], [x], [u(x)])
+    chain = Chain(Dense(1, 16, "sin"), Dense(16, 16, "softplus"), Dense(16, 16, "swish"), Dense(16, 1))
+    return Config("neumann_sin", sys_, [chain], GridTraining(1.0 / 63), n_pde_points=64)
+
+
+CASES = {
+    "cfg1": lambda: configs.config1(),
+    "cfg2_small": lambda: configs.config2(n=24, width=16, hidden=2),
+    "cfg3_small": lambda: configs.config3(points=512, bcs_points=96, width=32, hidden=3),
+    "cfg4_tiny": lambda: configs.config4(nodes=4, bc_nodes=3, width=16, hidden=2),
+    "cfg5_small": lambda: configs.config5(points=384, bcs_points=64, n_obs=80, width=16, hidden=2),
+    "mixed": mixed_derivative_case,
+    "neumann_sin": neumann_sin_case,
+}
+
+
+def point_sets(cfg: Config, seed: int = 11):
+    """Deterministic (d, N) float64 point sets [pde..., bc...] (+ quadrature weights / scales) of a case."""
+    sys_ = cfg.pde_system
+    vi = get_vars(sys_.ivs, sys_.dvs)
+    st = cfg.strategy
+    qw = qs = None
+    if isinstance(st, GridTraining):
+        ps, bs = generate_training_sets(sys_.domain, st.dx, sys_.eqs, sys_.bcs, np.float64, vi)
+        sets = ps + bs
+    elif isinstance(st, StochasticTraining):
+        pb, bb = get_bounds(sys_.domain, sys_.eqs, sys_.bcs, np.float64, vi, st)
+        rng = np.random.default_rng(seed)
+        sets = [generate_random_points(st.points, b, np.float64, rng) for b in pb] + \
+               [generate_random_points(st.bcs_points, b, np.float64, rng) for b in bb]
+    elif isinstance(st, QuasiRandomTraining):
+        pb, bb = get_bounds(sys_.domain, sys_.eqs, sys_.bcs, np.float64, vi, st)
+        sets = [generate_quasi_random_points(st.points, b, np.float64, seed + i) for i, b in enumerate(pb)] + \
+               [generate_quasi_random_points(st.bcs_points, b, np.float64, seed + 100 + i) for i, b in enumerate(bb)]
+    else:
+        pb, bb = get_bounds(sys_.domain, sys_.eqs, sys_.bcs, np.float64, vi, st)
+        sets, qw, qs = [], [], []
+        for i, b in enumerate(pb + bb):
+            n = st.nodes_per_dim if i < len(pb) else st.bc_nodes_per_dim
+            p, w, area = gauss_legendre_box(b, n, np.float64)
+            sets.append(p); qw.append(w); qs.append(1.0 / area)
+    return sets, qw, qs

@@ -9,7 +9,7 @@ def oracle_eval(cfg, theta64, derivative="exact", point_sets=None, quad=None):
     """Float64 oracle loss / term losses / gradient of a Config at the given point sets
     (default: the Grid sets the oracle itself generates)."""
     sys_ = cfg.pde_system
-    prob = R.Problem(sys_, cfg.oracle_chains(), param_estim=cfg.param_estim, derivative=derivative)
+    prob = R.Problem(sys_, cfg.chain_specs(), param_estim=cfg.param_estim, derivative=derivative)
     n_pde = len(sys_.eqs)
     if point_sets is None:
         ps, bs = R.generate_training_sets(sys_.domain, cfg.strategy.dx, sys_.eqs, sys_.bcs, sys_.ivs, sys_.dvs)
@@ -35,3 +35,23 @@ def engine_eval(cfg, dtype, mode="ffma", want_grad=True):
 def rel(a, b):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def load_golden(name):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    n = int(g["n_sets"])
+    sets = [g["set_%d" % i] for i in range(n)]
+    qw = [g["qw_%d" % i] for i in range(n)] if "qw_0" in g else None
+    return g, sets, qw
+
+
+def engine_eval_sets(cfg, dtype, sets, qw=None, mode="ffma", want_grad=True, theta=None):
+    """Engine loss / terms / grad of a Config at explicit point sets (overrides the strategy's sets)."""
+    disc = cfg.discretization(dtype=dtype, mode=mode)
+    rep = npde.symbolic_discretize(cfg.pde_system, disc)
+    th = rep.flat_init_params if theta is None else np.asarray(theta, dtype=dtype)
+    for i, s in enumerate(sets):
+        rep.engine.set_points_host(i, s, None if qw is None else qw[i])
+    total, terms, grad = rep.engine.loss_grad_host(th, None, want_grad)
+    return rep, total, terms, grad

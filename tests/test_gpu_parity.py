@@ -46,7 +46,7 @@ def test_residual_probe_matches_oracle():
     rep, *_ = engine_eval(cfg, np.float64, want_grad=False)
     from oracle import reference as R
     import torch
-    prob = R.Problem(cfg.pde_system, cfg.oracle_chains(), derivative="exact")
+    prob = R.Problem(cfg.pde_system, cfg.chain_specs(), derivative="exact")
     pts = rep.point_sets[0]
     r = rep.loss_functions.datafree_pde_loss_functions[0](pts, rep.flat_init_params)
     ro = prob.residual(cfg.pde_system.eqs[0], torch.as_tensor(pts), torch.as_tensor(rep.flat_init_params)).numpy()

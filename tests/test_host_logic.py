@@ -1,0 +1,158 @@
+"""Host-side mirror of the reference interface: variable bookkeeping, lowering, training sets, error
+behaviour.  CPU only (no engine calls)."""
+import numpy as np
+import pytest
+import sympy as sp
+
+import neuralpde_jl_b200 as npde
+from neuralpde_jl_b200 import configs
+from neuralpde_jl_b200.strategies import (GridTraining, QuadratureTraining, StochasticTraining, gauss_legendre_box,
+                                          generate_training_sets, get_bounds, shard_range)
+from oracle import reference as R
+from cases import CASES
+
+
+def _poisson():
+    cfg = configs.config2(n=8, width=16, hidden=2)
+    return cfg, npde.get_vars(cfg.pde_system.ivs, cfg.pde_system.dvs)
+
+
+def test_get_vars_and_arguments():
+    cfg, vi = _poisson()
+    assert vi.depvars == ["u"] and vi.indvars == ["x", "y"] and vi.dict_depvar_input == {"u": ["x", "y"]}
+    assert npde.get_argument(cfg.pde_system.eqs, vi) == [["x", "y"]]
+    assert npde.get_argument(cfg.pde_system.bcs, vi) == [[0.0, "y"], [1.0, "y"], ["x", 0.0], ["x", 1.0]]
+    assert npde.get_variables(cfg.pde_system.bcs, vi) == [["y"], ["y"], ["x"], ["x"]]
+    # same answers from the independent restatement in the oracle
+    s = cfg.pde_system
+    assert R.get_argument(s.bcs, s.ivs, s.dvs) == npde.get_argument(s.bcs, vi)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_training_sets_match_oracle(name):
+    cfg = CASES[name]()
+    if not isinstance(cfg.strategy, GridTraining):
+        pytest.skip("grid cases only")
+    s = cfg.pde_system
+    vi = npde.get_vars(s.ivs, s.dvs)
+    ps, bs = generate_training_sets(s.domain, cfg.strategy.dx, s.eqs, s.bcs, np.float64, vi)
+    po, bo = R.generate_training_sets(s.domain, cfg.strategy.dx, s.eqs, s.bcs, s.ivs, s.dvs)
+    for a, b in zip(ps + bs, po + bo):
+        np.testing.assert_array_equal(a, b)
+
+
+def test_grid_set_layout():
+    """(d, N) matrices, first variable fastest, bc constants substituted (reference src/discretize.jl:226-238);
+    the PDE set is the full grid because `dif` is never filled (:214-222)."""
+    cfg, vi = _poisson()
+    s = cfg.pde_system
+    ps, bs = generate_training_sets(s.domain, cfg.strategy.dx, s.eqs, s.bcs, np.float32, vi)
+    assert ps[0].shape == (2, 64) and ps[0].dtype == np.float32
+    assert ps[0][0, 1] > ps[0][0, 0] and ps[0][1, 1] == ps[0][1, 0]          # x fastest
+    assert ps[0][0].min() == 0.0 and ps[0][0].max() == 1.0                     # boundary points included
+    assert bs[0].shape == (2, 8) and np.all(bs[0][0] == 0.0) and np.all(bs[1][0] == 1.0)
+    assert np.all(bs[2][1] == 0.0) and np.all(bs[3][1] == 1.0)
+
+
+def test_bounds_stochastic_and_quadrature():
+    cfg = configs.config3(points=100, bcs_points=10)
+    s = cfg.pde_system
+    vi = npde.get_vars(s.ivs, s.dvs)
+    pb, bb = get_bounds(s.domain, s.eqs, s.bcs, np.float64, vi, cfg.strategy)
+    np.testing.assert_allclose(pb[0][0], [0.01, -0.99])
+    np.testing.assert_allclose(pb[0][1], [0.99, 0.99])
+    np.testing.assert_allclose(bb[0][0], [0.0, -0.99]); np.testing.assert_allclose(bb[0][1], [0.0, 0.99])   # u(0, x)
+    np.testing.assert_allclose(bb[1][0], [0.01, -1.0]); np.testing.assert_allclose(bb[1][1], [0.99, -1.0])  # u(t, -1)
+    po, bo = R.get_bounds(s.domain, s.eqs, s.bcs, s.ivs, s.dvs, 100)
+    for (a0, a1), (b0, b1) in zip(pb + bb, po + bo):
+        np.testing.assert_allclose(a0, b0); np.testing.assert_allclose(a1, b1)
+    pts, w, area = gauss_legendre_box((np.array([0.0, 2.0, 1.0]), np.array([1.0, 2.0, 3.0])), 5, np.float64)
+    assert pts.shape == (3, 25) and np.all(pts[1] == 2.0) and abs(w.sum() - 2.0) < 1e-13 and area == 2.0
+    # exact for polynomials of degree <= 9
+    assert abs(np.sum(w * pts[0] ** 8 * pts[2] ** 3) - (1 / 9) * (81 - 1) / 4) < 1e-12
+
+
+def test_lowering_poisson_program():
+    cfg, vi = _poisson()
+    lt = npde.lower_equation(cfg.pde_system.eqs[0], vi)
+    assert [(t.net, t.order, tuple(t.dirs)) for t in lt.taps] == [(0, 2, (0, 0)), (0, 2, (1, 1))]
+    assert lt.prog[-1][0] == "sub" and lt.indvars == ["x", "y"] and lt.net_rows == [[0, 1]]
+    lb = npde.lower_equation(cfg.pde_system.bcs[0], vi)
+    assert [(t.order,) for t in lb.taps] == [(0,)] and lb.indvars == ["x", "y"]
+
+
+def test_lowering_matches_oracle_residual_numerically():
+    """The IR program evaluated on the host equals the oracle's tree walk (taps supplied by the oracle)."""
+    import torch
+    cfg = CASES["neumann_sin"]()
+    s = cfg.pde_system
+    vi = npde.get_vars(s.ivs, s.dvs)
+    prob = R.Problem(s, cfg.chain_specs(), derivative="exact")
+    theta = torch.tensor(cfg.init_params(np.float64))
+    X = torch.linspace(0.05, 0.95, 7).reshape(1, -1)
+    lt = npde.lower_equation(s.eqs[0], vi)
+    dims, acts = cfg.chain_specs()[0]
+    taps = [R.exact_tap(X, theta, dims, acts, 0, tuple(t.dirs)).numpy()[0] for t in lt.taps]
+    val = []
+    for op, a, b, imm in lt.prog:
+        v = {"const": lambda: np.full(7, imm), "coord": lambda: X.numpy()[a], "tap": lambda: taps[a],
+             "add": lambda: val[a] + val[b], "sub": lambda: val[a] - val[b], "mul": lambda: val[a] * val[b],
+             "div": lambda: val[a] / val[b], "neg": lambda: -val[a], "powi": lambda: val[a] ** int(imm),
+             "sin": lambda: np.sin(val[a]), "cos": lambda: np.cos(val[a]), "exp": lambda: np.exp(val[a])}[op]()
+        val.append(v)
+    np.testing.assert_allclose(val[-1], prob.residual(s.eqs[0], X, theta).numpy()[0], rtol=1e-13)
+
+
+def test_error_behaviour_matches_reference():
+    x, y = npde.parameters("x y")
+    u = npde.variables("u")
+    D3 = npde.Differential(x) ** 3
+    vi = npde.get_vars([x, y], [u(x, y)])
+    # order-3 derivative: reference has a stencil (src/pinn_types.jl:469-474); the engine refuses loudly
+    with pytest.raises(npde.LoweringError, match="order 3"):
+        npde.lower_equation(npde.Eq(D3(u(x, y)), 0), vi)
+    # trivial bc 0 ~ 0 (reference: ArgumentError for sampling strategies,
+    # test/direct_function__trivial_bc_0_0_fails_for_some_training_strategies.jl:41-45)
+    with pytest.raises(npde.LoweringError, match="no dependent variable"):
+        npde.lower_equation(npde.Eq(0, 0), vi)
+    with pytest.raises(npde.LoweringError, match="unknown symbol"):
+        npde.lower_equation(npde.Eq(u(x, y), sp.Symbol("q")), vi)
+    # empty bcs (reference: solve throws, test/direct_function__empty_boundary_condition_fails_in_solve_phase.jl:15-25)
+    sys_ = npde.PDESystem(npde.Eq(u(x, y), 0), [], [npde.In(x, 0, 1), npde.In(y, 0, 1)], [x, y], [u(x, y)])
+    disc = npde.PhysicsInformedNN(npde.Chain(npde.Dense(2, 8, "tanh"), npde.Dense(8, 1)), GridTraining(0.5))
+    with pytest.raises(ValueError, match="no boundary conditions"):
+        npde.symbolic_discretize(sys_, disc)
+    with pytest.raises(ValueError, match="custom `derivative`"):
+        npde.PhysicsInformedNN(npde.Chain(npde.Dense(2, 8, "tanh"), npde.Dense(8, 1)), GridTraining(0.5), derivative=lambda *a: 0)
+
+
+def test_theta_layout_is_componentarray_order():
+    chain = npde.Chain(npde.Dense(2, 3, "tanh"), npde.Dense(3, 1))
+    th = npde.initialparameters(np.random.default_rng(0), chain)
+    assert th.size == 2 * 3 + 3 + 3 + 1 and np.all(th[6:9] == 0) and th[12] == 0
+    # weight is out x in column-major: the oracle's unpack reads it back
+    import torch
+    Ws, bs = R.unpack(torch.tensor(th), [2, 3, 1])
+    assert Ws[0].shape == (3, 2) and float(Ws[0][1, 0]) == th[1] and float(Ws[0][0, 1]) == th[3]
+
+
+def test_shard_range_partitions():
+    for n, w in ((10, 3), (16384, 8), (5, 8), (0, 2)):
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+
+
+def test_logging_hooks_noop_and_custom():
+    """reference test/qa/qa.jl:32-62: no-op fallback, custom logger methods."""
+    npde.logscalar(None, 1.0, "a", 1)
+    npde.logvector(None, [1.0], "a", 1)
+
+    class L:
+        def __init__(self): self.rows = []
+        def log_value(self, name, v, step): self.rows.append((name, v, step))
+    lg = L()
+    npde.logscalar(lg, 2.0, "loss", 3)
+    npde.logvector(lg, [1.0, 2.0], "w", 3)
+    assert lg.rows == [("loss", 2.0, 3), ("w/1", 1.0, 3), ("w/2", 2.0, 3)]
