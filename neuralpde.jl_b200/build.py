@@ -61,7 +61,13 @@ def _extra_units():
     return extra
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, tc_threads: int = 0) -> str:
+    """tc_threads != 0 builds an experimental variant library (libpinn_b200_t<N>.so) of the tcgen05 kernel."""
+    global OBJDIR, LIB
+    if tc_threads and "build_x" not in OBJDIR:
+        OBJDIR = os.path.join(HERE, "build_t%d" % tc_threads)
+        LIB = os.path.join(LIBDIR, "libpinn_b200_t%d.so" % tc_threads)
+        NVCC_FLAGS.append("-DPINN_TC_THREADS=%d" % tc_threads)
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = _nvcc()
@@ -95,4 +101,9 @@ def build(verbose: bool = False, force: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    for a in sys.argv:
+        if a.startswith("-X"):      # timing experiments: -XNO_LDTM etc. -> libpinn_b200_x<name>.so
+            OBJDIR = os.path.join(HERE, "build_x" + a[2:]); LIB = os.path.join(LIBDIR, "libpinn_b200_x%s.so" % a[2:])
+            NVCC_FLAGS.append("-DPINN_EXP_" + a[2:])
+    tt = [int(a[2:]) for a in sys.argv if a.startswith("-t")]
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, tc_threads=tt[0] if tt else 0))

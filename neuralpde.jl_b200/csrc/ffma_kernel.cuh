@@ -378,92 +378,108 @@ __device__ __forceinline__ void rebuild_h(real* H, const real* stash, const DevC
 
 // residual program: forward values and reverse adjoints, one point per lane (warp 0 only)
 // STRIDE = points per tile in the Xs / taps / tapbar arrays ([index][point])
-template <typename real, int STRIDE>
-__device__ __noinline__ real run_program(const DevTerm& tm, const real* theta_p, const real* Xs, const real* taps,
-                                          real* tapbar, real* pbar, int lane, bool want_adjoint) {
-  real val[PINN_MAX_INSTR];
-  const int n = tm.n_instr;
+// SM: the program text and the per-point value / adjoint arrays live in shared memory (sprog, sval, sadj:
+// [instr][point]) instead of global / local memory.
+template <typename real, int STRIDE, bool SM>
+__device__ __noinline__ real run_program_t(const DevInstr* prog, int n, const real* theta_p, const real* Xs, const real* taps,
+                                            real* tapbar, real* pbar, int lane, bool want_adjoint, real* sval, real* sadj) {
+  real lval[SM ? 1 : PINN_MAX_INSTR];
+  real ladj[SM ? 1 : PINN_MAX_INSTR];
+  real* val = SM ? (sval + lane) : lval;
+  real* adj = SM ? (sadj + lane) : ladj;
+  constexpr int VS = SM ? STRIDE : 1;
+#define PV(i) val[(i) * VS]
+#define PA(i) adj[(i) * VS]
   for (int i = 0; i < n; ++i) {
-    const DevInstr& in = tm.prog[i];
+    const DevInstr& in = prog[i];
     real v;
     switch (in.op) {
       case PINN_OP_CONST: v = real(in.imm); break;
       case PINN_OP_COORD: v = Xs[in.a * STRIDE + lane]; break;
       case PINN_OP_TAP: v = taps[in.a * STRIDE + lane]; break;
       case PINN_OP_PARAM: v = theta_p[in.a]; break;
-      case PINN_OP_ADD: v = val[in.a] + val[in.b]; break;
-      case PINN_OP_SUB: v = val[in.a] - val[in.b]; break;
-      case PINN_OP_MUL: v = val[in.a] * val[in.b]; break;
-      case PINN_OP_DIV: v = val[in.a] / val[in.b]; break;
-      case PINN_OP_NEG: v = -val[in.a]; break;
-      case PINN_OP_POW: v = m_pow(val[in.a], val[in.b]); break;
+      case PINN_OP_ADD: v = PV(in.a) + PV(in.b); break;
+      case PINN_OP_SUB: v = PV(in.a) - PV(in.b); break;
+      case PINN_OP_MUL: v = PV(in.a) * PV(in.b); break;
+      case PINN_OP_DIV: v = PV(in.a) / PV(in.b); break;
+      case PINN_OP_NEG: v = -PV(in.a); break;
+      case PINN_OP_POW: v = m_pow(PV(in.a), PV(in.b)); break;
       case PINN_OP_POWI: {
         int e = (int)in.imm;
-        real b = val[in.a], r = real(1);
+        real b = PV(in.a), r = real(1);
         int ae = e < 0 ? -e : e;
         while (ae) { if (ae & 1) r *= b; b *= b; ae >>= 1; }
         v = e < 0 ? real(1) / r : r;
       } break;
-      case PINN_OP_SIN: v = m_sin(val[in.a]); break;
-      case PINN_OP_COS: v = m_cos(val[in.a]); break;
-      case PINN_OP_EXP: v = m_exp(val[in.a]); break;
-      case PINN_OP_LOG: v = m_log(val[in.a]); break;
-      case PINN_OP_TANH: v = m_tanh(val[in.a]); break;
-      case PINN_OP_SQRT: v = m_sqrt(val[in.a]); break;
-      case PINN_OP_ABS: v = m_abs(val[in.a]); break;
+      case PINN_OP_SIN: v = m_sin(PV(in.a)); break;
+      case PINN_OP_COS: v = m_cos(PV(in.a)); break;
+      case PINN_OP_EXP: v = m_exp(PV(in.a)); break;
+      case PINN_OP_LOG: v = m_log(PV(in.a)); break;
+      case PINN_OP_TANH: v = m_tanh(PV(in.a)); break;
+      case PINN_OP_SQRT: v = m_sqrt(PV(in.a)); break;
+      case PINN_OP_ABS: v = m_abs(PV(in.a)); break;
       default: v = real(0);
     }
-    val[i] = v;
+    PV(i) = v;
   }
-  const real r = val[n - 1];
+  const real r = PV(n - 1);
   if (!want_adjoint) return r;
 
-  real adj[PINN_MAX_INSTR];
-  for (int i = 0; i < n; ++i) adj[i] = real(0);
-  adj[n - 1] = real(1);
+  for (int i = 0; i < n; ++i) PA(i) = real(0);
+  PA(n - 1) = real(1);
   for (int i = n - 1; i >= 0; --i) {
-    const DevInstr& in = tm.prog[i];
-    const real g = adj[i];
+    const DevInstr& in = prog[i];
+    const real g = PA(i);
     switch (in.op) {
       case PINN_OP_TAP: tapbar[in.a * STRIDE + lane] += g; break;
       case PINN_OP_PARAM: pbar[in.a] += g; break;
-      case PINN_OP_ADD: adj[in.a] += g; adj[in.b] += g; break;
-      case PINN_OP_SUB: adj[in.a] += g; adj[in.b] -= g; break;
-      case PINN_OP_MUL: adj[in.a] += g * val[in.b]; adj[in.b] += g * val[in.a]; break;
+      case PINN_OP_ADD: PA(in.a) += g; PA(in.b) += g; break;
+      case PINN_OP_SUB: PA(in.a) += g; PA(in.b) -= g; break;
+      case PINN_OP_MUL: PA(in.a) += g * PV(in.b); PA(in.b) += g * PV(in.a); break;
       case PINN_OP_DIV: {
-        real inv = real(1) / val[in.b];
-        adj[in.a] += g * inv;
-        adj[in.b] -= g * val[i] * inv;
+        real inv = real(1) / PV(in.b);
+        PA(in.a) += g * inv;
+        PA(in.b) -= g * PV(i) * inv;
       } break;
-      case PINN_OP_NEG: adj[in.a] -= g; break;
+      case PINN_OP_NEG: PA(in.a) -= g; break;
       case PINN_OP_POW: {
-        real x = val[in.a], y = val[in.b];
-        adj[in.a] += g * y * m_pow(x, y - real(1));
-        if (x > real(0)) adj[in.b] += g * val[i] * m_log(x);
+        real x = PV(in.a), y = PV(in.b);
+        PA(in.a) += g * y * m_pow(x, y - real(1));
+        if (x > real(0)) PA(in.b) += g * PV(i) * m_log(x);
       } break;
       case PINN_OP_POWI: {
         int e = (int)in.imm;
         if (e != 0) {
-          real b = val[in.a], rr = real(1);
+          real b = PV(in.a), rr = real(1);
           int e1 = e - 1;
           int ae = e1 < 0 ? -e1 : e1;
           real bb = b;
           while (ae) { if (ae & 1) rr *= bb; bb *= bb; ae >>= 1; }
           if (e1 < 0) rr = real(1) / rr;
-          adj[in.a] += g * real(e) * rr;
+          PA(in.a) += g * real(e) * rr;
         }
       } break;
-      case PINN_OP_SIN: adj[in.a] += g * m_cos(val[in.a]); break;
-      case PINN_OP_COS: adj[in.a] -= g * m_sin(val[in.a]); break;
-      case PINN_OP_EXP: adj[in.a] += g * val[i]; break;
-      case PINN_OP_LOG: adj[in.a] += g / val[in.a]; break;
-      case PINN_OP_TANH: adj[in.a] += g * (real(1) - val[i] * val[i]); break;
-      case PINN_OP_SQRT: adj[in.a] += g * real(0.5) / val[i]; break;
-      case PINN_OP_ABS: adj[in.a] += (val[in.a] >= real(0)) ? g : -g; break;
+      case PINN_OP_SIN: PA(in.a) += g * m_cos(PV(in.a)); break;
+      case PINN_OP_COS: PA(in.a) -= g * m_sin(PV(in.a)); break;
+      case PINN_OP_EXP: PA(in.a) += g * PV(i); break;
+      case PINN_OP_LOG: PA(in.a) += g / PV(in.a); break;
+      case PINN_OP_TANH: PA(in.a) += g * (real(1) - PV(i) * PV(i)); break;
+      case PINN_OP_SQRT: PA(in.a) += g * real(0.5) / PV(i); break;
+      case PINN_OP_ABS: PA(in.a) += (PV(in.a) >= real(0)) ? g : -g; break;
       default: break;
     }
   }
   return r;
+#undef PV
+#undef PA
+}
+
+// STRIDE = points per tile in the Xs / taps / tapbar arrays ([index][point]); program read from the term
+template <typename real, int STRIDE>
+__device__ __forceinline__ real run_program(const DevTerm& tm, const real* theta_p, const real* Xs, const real* taps,
+                                            real* tapbar, real* pbar, int lane, bool want_adjoint) {
+  return run_program_t<real, STRIDE, false>(tm.prog, tm.n_instr, theta_p, Xs, taps, tapbar, pbar, lane, want_adjoint,
+                                            (real*)nullptr, (real*)nullptr);
 }
 
 template <typename real>

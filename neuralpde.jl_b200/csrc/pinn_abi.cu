@@ -99,6 +99,7 @@ struct pinn_engine {
   int tc_split = 0, tc_tl_max = 0, tc_off_P = 0, tc_off_Q = 0, tc_off_misc = 0;
   TcNetSmem tc_nets[PINN_MAX_NETS];
   long long tc_stash_per_cta = 0;
+  long long* tc_dbg = nullptr;   // device buffer for pinn_debug_tc_timeline
   // workspaces (device)
   void* partial = nullptr;
   double* term_sums = nullptr;
@@ -645,6 +646,8 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
   t.stash = (uint8_t*)e->stash; t.stash_per_cta = e->tc_stash_per_cta; t.split = e->tc_split; t.tl_max = std::max(e->tc_tl_max, 1);
   t.tile_begin = a.tile_begin; t.tile_end = a.tile_end; t.mode = a.mode; t.resid_out = (float*)a.resid_out;
   t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc;
+  t.dbg = e->tc_dbg;
+  t.off_Q_bytes = e->tc_off_Q - e->tc_off_P;   // P and Q regions have the same size
   for (int k = 0; k < PINN_MAX_NETS; ++k) {
     t.nets[k] = e->tc_nets[k];
     int ak = 1;
@@ -788,6 +791,22 @@ int pinn_comm_init(pinn_handle e, const void* uid, int32_t rank, int32_t nranks)
   ncclResult_t r = g_nccl.CommInitRank(&e->comm, nranks, id, rank);
   if (r != 0) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   e->rank = rank; e->nranks = nranks;
+  return 0;
+}
+
+// diagnostic (not part of the drop-in ABI): enable phase timestamps of CTA 0 in the tcgen05 kernel and
+// read them back (1000 x int64: id << 48 | clock); host_out == NULL only enables.
+int pinn_debug_tc_timeline(pinn_handle e, long long* host_out) {
+  if (!e) return fail("pinn_debug_tc_timeline: null handle");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!e->tc_dbg) {
+    CUDA_TRY(cudaMalloc((void**)&e->tc_dbg, 1000 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(e->tc_dbg, 0, 1000 * sizeof(long long)));
+  }
+  if (host_out) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(host_out, e->tc_dbg, 1000 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
   return 0;
 }
 

@@ -49,6 +49,9 @@ __device__ __forceinline__ void add_at(float* v, int idx, float x) {
 // AK = 0: any activation through the accurate generic evaluator.
 template <int AK>
 __device__ __forceinline__ void act_eval_tc(int act, float z, float& a, float& d1, float& d2, float& d3) {
+#ifdef PINN_EXP_NO_ACT
+  a = z; d1 = 1.f; d2 = 0.5f; d3 = 0.25f; return;
+#endif
   if (AK == 1) {
     const float e = __expf(2.f * z);
     const float t = 1.f - __fdividef(2.f, e + 1.f);
@@ -68,6 +71,10 @@ __device__ __forceinline__ int act_kind(int act) { return act == PINN_ACT_TANH ?
 // also the bf16 residual v - bf16(v) into the lo tile
 __device__ __forceinline__ void store_half(uint8_t* tile_hi, uint8_t* tile_lo, int row, int col0, const float (&v)[4],
                                            bool split) {
+#ifdef PINN_EXP_NO_STS
+  asm volatile("" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]));
+  return;
+#endif
   const uint32_t off = tc::swz_chunk(row, col0 >> 3) + ((col0 & 4) << 1);
   uint2 h;
   h.x = tc::pack_bf16(v[0], v[1]); h.y = tc::pack_bf16(v[2], v[3]);
@@ -81,6 +88,10 @@ __device__ __forceinline__ void store_half(uint8_t* tile_hi, uint8_t* tile_lo, i
 }
 
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+#ifdef PINN_EXP_NO_LDTM
+  v[0] = __uint_as_float(taddr & 0x3fffffu) * 1e-9f; v[1] = v[0] + 1e-3f; v[2] = v[0] - 1e-3f; v[3] = v[0] * 0.5f;
+  return;
+#endif
   uint32_t r[4];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -148,6 +159,9 @@ __device__ __forceinline__ void chain_bwd(int act, const Chan<N1, N2>& ch, const
 // sum over the 32 lanes of 4 per-lane values with 6 shuffles.  Every lane receives the total of
 // element e = ((lane>>4)&1)*2 + ((lane>>3)&1); lanes with (lane & 7) == 0 act on it.
 __device__ __forceinline__ float warp_reduce4(const float (&v)[4], int lane) {
+#ifdef PINN_EXP_NO_RED
+  return v[0] + v[1] + v[2] + v[3];
+#endif
   const bool up16 = (lane & 16) != 0;
   float a0 = (up16 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[2], 16);
   float a1 = (up16 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, up16 ? v[1] : v[3], 16);
@@ -168,8 +182,17 @@ struct CtaShared {
   float* partial;
   uint8_t* stash;
   const float* theta;
+  long long* dbg;          // optional phase-timestamp buffer (CTA 0, thread 0)
+  int dbg_n;
   TcNetSmem nets[PINN_MAX_NETS];
 };
+
+// phase timestamps for the timeline tool (scripts/tc_timeline.py): id in the high bits, clock in the low
+__device__ __forceinline__ void dbg_mark(CtaShared* cs, int id) {
+  if (cs->dbg && threadIdx.x == 0 && cs->dbg_n < 1000) {
+    cs->dbg[cs->dbg_n++] = ((long long)id << 48) | (clock64() & 0xffffffffffffLL);
+  }
+}
 
 struct Misc {   // carve-up of the misc region
   float *Xs, *taps, *tapbar, *scratch, *qws, *rres;
@@ -268,10 +291,8 @@ struct LoopCtx {
 
 // layer 0 forward: coordinates -> H^0 tiles (+ last-layer dot when there is no tensor layer: flag)
 template <int N1, int N2, bool PURE, int AK>
-__device__ __forceinline__ void l0_fwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, const float* xp, float* up) {
+__device__ __forceinline__ void l0_fwd_loop(const LoopCtx lc, const PassInfo<N1, N2> pi, const float* xp, float* up) {
   constexpr int C = 1 + N1 + N2;
-  const LoopCtx& lc = *lcp;
-  const PassInfo<N1, N2>& pi = *pip;
   float x[PINN_MAX_IN], u[C];
 #pragma unroll
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = xp[k];
@@ -302,10 +323,8 @@ __device__ __forceinline__ void l0_fwd_loop(const LoopCtx* lcp, const PassInfo<N
 
 // tensor layer forward epilogue: TMEM accumulators -> bias + activation chain -> next operand tiles
 template <int N1, int N2, bool PURE, int AK>
-__device__ __forceinline__ void tl_fwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, float* up) {
+__device__ __forceinline__ void tl_fwd_loop(const LoopCtx lc, const Chan<N1, N2> ch, float* up) {
   constexpr int C = 1 + N1 + N2;
-  const LoopCtx& lc = *lcp;
-  const Chan<N1, N2>& ch = pip->ch;
   float u[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) u[c] = up[c];
@@ -340,10 +359,8 @@ __device__ __forceinline__ void tl_fwd_loop(const LoopCtx* lcp, const PassInfo<N
 // tensor layer backward epilogue for the column group starting at c0: recomputed Z (TMEM Y) and output
 // adjoints (TMEM X, or w_last * ubar for the last hidden layer: flag) -> Zbar tiles + bias gradient
 template <int N1, int N2, bool PURE, int AK>
-__device__ __forceinline__ void tl_bwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, const float* ubp) {
+__device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2> ch, const float* ubp) {
   constexpr int C = 1 + N1 + N2;
-  const LoopCtx& lc = *lcp;
-  const Chan<N1, N2>& ch = pip->ch;
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
@@ -391,10 +408,8 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx* lcp, const PassInfo<N
 
 // layer 0 backward: adjoints of H^0 (TMEM X, or w_last * ubar: flag) -> first-layer weight / bias gradient
 template <int N1, int N2, bool PURE, int AK>
-__device__ __forceinline__ void l0_bwd_loop(const LoopCtx* lcp, const PassInfo<N1, N2>* pip, const float* xp, const float* ubp) {
+__device__ __forceinline__ void l0_bwd_loop(const LoopCtx lc, const PassInfo<N1, N2> pi, const float* xp, const float* ubp) {
   constexpr int C = 1 + N1 + N2;
-  const LoopCtx& lc = *lcp;
-  const PassInfo<N1, N2>& pi = *pip;
   float x[PINN_MAX_IN], ub[C];
 #pragma unroll
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = xp[k];
@@ -455,7 +470,7 @@ __device__ __forceinline__ void l0_bwd_loop(const LoopCtx* lcp, const PassInfo<N
 // forward of one network for the current tile, channel structure <N1, N2, PURE>.
 // `phase` bit 0 = parity of the MMA barrier, bit 1 = parity of the bulk-load barrier; returned updated.
 template <int N1, int N2, bool PURE, int AK>
-__device__ __noinline__ uint32_t net_forward(const CtaShared* cs, const DevProblem* Pp, const DevTerm* tmp, int slot,
+__device__ __noinline__ uint32_t net_forward(CtaShared* cs, const DevProblem* Pp, const DevTerm* tmp, int slot,
                                              int want_grad, uint32_t phase) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int C = 1 + N1 + N2;
@@ -481,6 +496,7 @@ __device__ __noinline__ uint32_t net_forward(const CtaShared* cs, const DevProbl
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < pi.d_in) ? ms.Xs[dc.rows[k] * kTcPts + p] : 0.f;
   uint8_t* stash_slot = cs->stash + (size_t)slot * cs->tl_max * kTcMaxC * kTileBytes;
 
+  dbg_mark(cs, 10);
   float u[C];                                   // last-layer partial dot products of this thread
 #pragma unroll
   for (int c = 0; c < C; ++c) u[c] = 0.f;
@@ -496,7 +512,7 @@ __device__ __noinline__ uint32_t net_forward(const CtaShared* cs, const DevProbl
     lc.fp = fp; lc.bt = fp; lc.tP = tP; lc.tQ = tQ; lc.gb = nullptr; lc.gw = nullptr; lc.taddr = tmem + t.lane_addr;
     lc.act = act0; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
     lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
-    l0_fwd_loop<N1, N2, PURE, AK>(&lc, &pi, x, u);
+    l0_fwd_loop<N1, N2, PURE, AK>(lc, pi, x, u);
   }
   // ---- tensor layers -------------------------------------------------------------------------------------
   for (int l = 1; l <= TL; ++l) {
@@ -505,43 +521,58 @@ __device__ __noinline__ uint32_t net_forward(const CtaShared* cs, const DevProbl
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc::tc_fence_after();
-      if (want_grad) {
-        for (int c = 0; c < C; ++c)
-          tc::bulk_store(stash_slot + (size_t)((l - 1) * kTcMaxC + c) * kTileBytes, tP + c * kTileBytes, kTileBytes);
-        tc::bulk_commit();
-      }
-      const uint32_t idesc = tc::make_idesc(128, n_out, 0, 0);
-      const uint32_t whi = tc::smem_u32(smem + ns.w_hi[l - 1]), wlo = tc::smem_u32(smem + ns.w_lo[l - 1]);
-      const uint64_t dwhi = tc::make_desc(whi, 0, 1024), dwlo = tc::make_desc(wlo, 0, 1024);
-      const int nk = n_in / 16;
+    dbg_mark(cs, 11);
+    if (tc::uni(t.warp) == 0) {
+      // warp-uniform issue path: every operand is made uniform, one elected lane issues
+      const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_Q = tc::uni(tc::smem_u32(tQ));
+      const uint32_t u_whi = tc::uni(tc::smem_u32(smem + ns.w_hi[l - 1])), u_wlo = tc::uni(tc::smem_u32(smem + ns.w_lo[l - 1]));
+      const int u_nk = tc::uni(n_in / 16), u_nout = tc::uni(n_out), u_split = tc::uni(split ? 1 : 0), u_wg = tc::uni(want_grad);
+      const uint64_t u_stash = tc::uni((uint64_t)(stash_slot + (size_t)(l - 1) * kTcMaxC * kTileBytes));
+      if (tc::elect_one()) {
+        tc::tc_fence_after();
+        if (u_wg) {
 #pragma unroll 1
-      for (int c = 0; c < C; ++c) {
-        const uint64_t dahi = tc::make_desc(tc::smem_u32(tP + c * kTileBytes), 0, 1024);
-        const uint32_t d = tmem + TM_X + c * 64;
-        mma_chain(d, dahi, dwhi, 32, 32, nk, idesc, 0);
-        if (split) {
-          const uint64_t dalo = tc::make_desc(tc::smem_u32(tQ + c * kTileBytes), 0, 1024);
-          mma_chain(d, dahi, dwlo, 32, 32, nk, idesc, 1);
-          mma_chain(d, dalo, dwhi, 32, 32, nk, idesc, 1);
+          for (int c = 0; c < C; ++c)
+            tc::bulk_store_u((void*)(u_stash + (uint64_t)c * kTileBytes), u_P + c * kTileBytes, kTileBytes);
+          tc::bulk_commit();
         }
+        const uint32_t idesc = tc::make_idesc(128, u_nout, 0, 0);
+        const uint64_t dwhi = tc::make_desc(u_whi, 0, 1024), dwlo = tc::make_desc(u_wlo, 0, 1024);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+          const uint64_t dahi = tc::make_desc(u_P + c * kTileBytes, 0, 1024);
+          const uint32_t d = u_tmem + TM_X + c * 64;
+          mma_chain(d, dahi, dwhi, 32, 32, u_nk, idesc, 0);
+          if (u_split) {
+            const uint64_t dalo = tc::make_desc(u_Q + c * kTileBytes, 0, 1024);
+            mma_chain(d, dahi, dwlo, 32, 32, u_nk, idesc, 1);
+            mma_chain(d, dalo, dwhi, 32, 32, u_nk, idesc, 1);
+          }
+        }
+        tc::mma_commit(ms.bar_mma);
       }
-      tc::mma_commit(ms.bar_mma);
+      __syncwarp();
     }
+    dbg_mark(cs, 12);
     wait_bar(ms.bar_mma, mma_phase);
     tc::tc_fence_after();
-    if (tid == 0 && want_grad) tc::bulk_wait_read0();   // stash copies have finished reading P
+    dbg_mark(cs, 13);
+    if (want_grad && tc::uni(t.warp) == 0) {
+      if (tc::elect_one()) tc::bulk_wait_read0();       // stash copies have finished reading P (same lane issued them)
+      __syncwarp();
+    }
     __syncthreads();
+    dbg_mark(cs, 14);
     const int ng = n_out / 4;
     LoopCtx lc;
     lc.fp = fp; lc.bt = fp + FP_BT + (l - 1) * 64; lc.tP = tP; lc.tQ = tQ; lc.gb = nullptr; lc.gw = nullptr;
     lc.taddr = tmem + t.lane_addr; lc.act = act; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane;
     lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH); lc.c0 = 0; lc.flag = (l == TL) ? 1 : 0;
-    tl_fwd_loop<N1, N2, PURE, AK>(&lc, &pi, u);
+    tl_fwd_loop<N1, N2, PURE, AK>(lc, pi.ch, u);
   }
   // ---- last layer (n -> 1, identity): combine the column parts of every point ---------------------------------
   __syncthreads();   // scratch zeroed
+  dbg_mark(cs, 15);
 #pragma unroll
   for (int c = 0; c < C; ++c) atomicAdd(&ms.scratch[c * kTcPts + p], u[c]);
   __syncthreads();
@@ -560,12 +591,13 @@ __device__ __noinline__ uint32_t net_forward(const CtaShared* cs, const DevProbl
       }
   }
   __syncthreads();
+  dbg_mark(cs, 16);
   return (phase & 2u) | mma_phase;
 }
 
 // reverse sweep of one network for the current tile
 template <int N1, int N2, bool PURE, int AK>
-__device__ __noinline__ uint32_t net_backward(const CtaShared* cs, const DevProblem* Pp, const DevTerm* tmp, int slot,
+__device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* Pp, const DevTerm* tmp, int slot,
                                               uint32_t phase) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int C = 1 + N1 + N2;
@@ -591,6 +623,7 @@ __device__ __noinline__ uint32_t net_backward(const CtaShared* cs, const DevProb
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < pi.d_in) ? ms.Xs[dc.rows[k] * kTcPts + p] : 0.f;
   uint8_t* stash_slot = cs->stash + (size_t)slot * cs->tl_max * kTcMaxC * kTileBytes;
 
+  dbg_mark(cs, 20);
   // adjoint of the network outputs per channel (every thread of the point needs it)
   float ub[C];
 #pragma unroll
@@ -660,59 +693,81 @@ __device__ __noinline__ uint32_t net_backward(const CtaShared* cs, const DevProb
     float* gw = partial + net.w_off[l];
     const float* bt = fp + FP_BT + (l - 1) * 64;
     const uint32_t whi = tc::smem_u32(smem + ns.w_hi[l - 1]);
-    if (tid == 0) {
+    dbg_mark(cs, 21);
+    if (tc::uni(t.warp) == 0) {
       // reload this layer's input tiles H^{l-1} (bf16 hi) from the stash into Q
-      tc::mbar_arrive_expect_tx(ms.bar_ld, C * kTileBytes);
-      for (int c = 0; c < C; ++c)
-        tc::bulk_load(tQ + c * kTileBytes, stash_slot + (size_t)((l - 1) * kTcMaxC + c) * kTileBytes, kTileBytes, ms.bar_ld);
+      const uint32_t u_Q = tc::uni(tc::smem_u32(tQ)), u_bar = tc::uni(tc::smem_u32(ms.bar_ld));
+      const uint64_t u_stash = tc::uni((uint64_t)(stash_slot + (size_t)(l - 1) * kTcMaxC * kTileBytes));
+      if (tc::elect_one()) {
+        tc::mbar_arrive_expect_tx_u(u_bar, C * kTileBytes);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c)
+          tc::bulk_load_u(u_Q + c * kTileBytes, (const void*)(u_stash + (uint64_t)c * kTileBytes), kTileBytes, u_bar);
+      }
+      __syncwarp();
     }
     wait_bar(ms.bar_ld, ld_phase);
+    dbg_mark(cs, 22);
     // recompute pre-activations in groups of <= 32 columns and turn output adjoints into Zbar tiles
     for (int c0 = 0; c0 < n_out; c0 += 32) {
       const int gw_cols = (n_out - c0) < 32 ? (n_out - c0) : 32;     // 32 or 16
       tc::tc_fence_before();
       __syncthreads();
-      if (tid == 0) {
-        tc::tc_fence_after();
-        const uint32_t idesc = tc::make_idesc(128, gw_cols, 0, 0);
-        const uint64_t dw = tc::make_desc(whi + c0 * 128, 0, 1024);
+      dbg_mark(cs, 23);
+      if (tc::uni(t.warp) == 0) {
+        const uint32_t u_tmem = tc::uni(tmem), u_Q = tc::uni(tc::smem_u32(tQ)), u_w = tc::uni(whi + c0 * 128);
+        const int u_nk = tc::uni(n_in / 16), u_gw = tc::uni(gw_cols);
+        if (tc::elect_one()) {
+          tc::tc_fence_after();
+          const uint32_t idesc = tc::make_idesc(128, u_gw, 0, 0);
+          const uint64_t dw = tc::make_desc(u_w, 0, 1024);
 #pragma unroll 1
-        for (int c = 0; c < C; ++c)
-          mma_chain(tmem + TM_Y + c * 32, tc::make_desc(tc::smem_u32(tQ + c * kTileBytes), 0, 1024), dw, 32, 32, n_in / 16,
-                    idesc, 0);
-        tc::mma_commit(ms.bar_mma);
+          for (int c = 0; c < C; ++c)
+            mma_chain(u_tmem + TM_Y + c * 32, tc::make_desc(u_Q + c * kTileBytes, 0, 1024), dw, 32, 32, u_nk, idesc, 0);
+          tc::mma_commit(ms.bar_mma);
+        }
+        __syncwarp();
       }
+      dbg_mark(cs, 24);
       wait_bar(ms.bar_mma, mma_phase);
       tc::tc_fence_after();
+      dbg_mark(cs, 25);
       const int ng = gw_cols / 4;
       LoopCtx lc;
       lc.fp = fp; lc.bt = bt; lc.tP = tP; lc.tQ = tQ; lc.gb = gb; lc.gw = nullptr; lc.taddr = tmem + t.lane_addr;
       lc.act = act; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
       lc.c0 = c0; lc.flag = (l == TL) ? 1 : 0;
-      tl_bwd_loop<N1, N2, PURE, AK>(&lc, &pi, ub);
+      tl_bwd_loop<N1, N2, PURE, AK>(lc, pi.ch, ub);
     }
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc::tc_fence_after();
-      // dgrad: Hbar_c = Zbar_c * W_l  -> X
-      const uint32_t idg = tc::make_idesc(128, n_in, 0, 1);
-      const uint64_t dw = tc::make_desc(whi, 0, 1024);
+    dbg_mark(cs, 26);
+    if (tc::uni(t.warp) == 0) {
+      const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_Q = tc::uni(tc::smem_u32(tQ)), u_w = tc::uni(whi);
+      const int u_nin = tc::uni(n_in), u_nko = tc::uni(n_out / 16);
+      if (tc::elect_one()) {
+        tc::tc_fence_after();
+        // dgrad: Hbar_c = Zbar_c * W_l  -> X
+        const uint32_t idg = tc::make_idesc(128, u_nin, 0, 1);
+        const uint64_t dw = tc::make_desc(u_w, 0, 1024);
 #pragma unroll 1
-      for (int c = 0; c < C; ++c)
-        mma_chain(tmem + TM_X + c * 64, tc::make_desc(tc::smem_u32(tP + c * kTileBytes), 0, 1024), dw, 32, 2048, n_out / 16,
-                  idg, 0);
-      // wgrad: Wbar_l = sum_c Zbar_c^T * H_c -> Y (rows >= 64 alias rows - 64 through LBO = 0)
-      const uint32_t iwg = tc::make_idesc(128, n_in, 1, 1);
+        for (int c = 0; c < C; ++c)
+          mma_chain(u_tmem + TM_X + c * 64, tc::make_desc(u_P + c * kTileBytes, 0, 1024), dw, 32, 2048, u_nko, idg, 0);
+        // wgrad: Wbar_l = sum_c Zbar_c^T * H_c -> Y (rows >= 64 alias rows - 64 through LBO = 0)
+        const uint32_t iwg = tc::make_idesc(128, u_nin, 1, 1);
 #pragma unroll 1
-      for (int c = 0; c < C; ++c)
-        mma_chain(tmem + TM_Y, tc::make_desc(tc::smem_u32(tP + c * kTileBytes), 0, 1024),
-                  tc::make_desc(tc::smem_u32(tQ + c * kTileBytes), 0, 1024), 2048, 2048, kTcPts / 16, iwg, c > 0 ? 1u : 0u);
-      tc::mma_commit(ms.bar_mma);
+        for (int c = 0; c < C; ++c)
+          mma_chain(u_tmem + TM_Y, tc::make_desc(u_P + c * kTileBytes, 0, 1024), tc::make_desc(u_Q + c * kTileBytes, 0, 1024),
+                    2048, 2048, kTcPts / 16, iwg, c > 0 ? 1u : 0u);
+        tc::mma_commit(ms.bar_mma);
+      }
+      __syncwarp();
     }
+    dbg_mark(cs, 27);
     wait_bar(ms.bar_mma, mma_phase);
     tc::tc_fence_after();
+    dbg_mark(cs, 28);
     // flush the weight-gradient tile: TMEM lane = output neuron o, column = input neuron k
     if (q < 2) {
       const int o = q * 32 + lane;
@@ -735,6 +790,7 @@ __device__ __noinline__ uint32_t net_backward(const CtaShared* cs, const DevProb
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
+    dbg_mark(cs, 29);
     const int act0 = net.acts[0];
     float* gb0 = partial + net.b_off[0];
     float* gw0 = partial + net.w_off[0];
@@ -743,9 +799,10 @@ __device__ __noinline__ uint32_t net_backward(const CtaShared* cs, const DevProb
     lc.fp = fp; lc.bt = fp; lc.tP = tP; lc.tQ = tQ; lc.gb = gb0; lc.gw = gw0; lc.taddr = tmem + t.lane_addr;
     lc.act = act0; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
     lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
-    l0_bwd_loop<N1, N2, PURE, AK>(&lc, &pi, x, ub);
+    l0_bwd_loop<N1, N2, PURE, AK>(lc, pi, x, ub);
   }
   __syncthreads();
+  dbg_mark(cs, 30);
   return (ld_phase << 1) | mma_phase;
 }
 
@@ -798,7 +855,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     cs.off_misc = args.off_misc; cs.partial = partial;
     cs.stash = args.stash + (long long)blockIdx.x * args.stash_per_cta;
     cs.theta = theta;
+    cs.dbg = (blockIdx.x == 0) ? args.dbg : nullptr;
+    cs.dbg_n = 0;
     for (int k = 0; k < PINN_MAX_NETS; ++k) cs.nets[k] = args.nets[k];
+    if (cs.dbg) cs.dbg[cs.dbg_n++] = ((long long)1 << 48) | (clock64() & 0xffffffffffffLL);
   }
   if (warp == 0) tc::tmem_alloc<512>(ms.tmem_slot);
   if (want_grad) {
@@ -867,6 +927,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
   tc::tc_fence_after();
   if (tid == 0) cs.tmem = *ms.tmem_slot;
   __syncthreads();
+  dbg_mark(&cs, 2);
   uint32_t phase = 0;
 
   for (int tile = args.tile_begin + blockIdx.x; tile < args.tile_end; tile += gridDim.x) {
@@ -878,6 +939,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     const long long n_pts = args.dyn[ti].n;
     const float* pts = reinterpret_cast<const float*>(args.dyn[ti].pts);
     const float* qw = reinterpret_cast<const float*>(args.dyn[ti].qw);
+    // warm L1 with the term header + residual program and the network descriptors (read by every phase)
+    if (tid < (int)((sizeof(DevTerm) + 127) / 128)) tc::prefetch_l1(reinterpret_cast<const char*>(tmp) + tid * 128);
+    if (tid >= 128 && tid < 128 + (int)((sizeof(DevNet) * PINN_MAX_NETS + 127) / 128))
+      tc::prefetch_l1(reinterpret_cast<const char*>(&P.nets[0]) + (tid - 128) * 128);
     const int dim = tm.dim, n_taps = tm.n_taps, n_used = tm.n_used, weighted = tm.weighted;
     for (int i = tid; i < dim * kTcPts; i += kTcThreads) {
       int pp = i / dim, r = i - pp * dim;
@@ -893,6 +958,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     }
     for (int i = tid; i < n_taps * kTcPts; i += kTcThreads) ms.tapbar[i] = 0.f;
     __syncthreads();
+    dbg_mark(&cs, 3);
 
     for (int slot = 0; slot < n_used; ++slot) {
       const int k1 = tm.chan[slot].n1, k2 = tm.chan[slot].n2, pu = tm.chan[slot].pure;
@@ -900,12 +966,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
       PINN_TC_DISPATCH(k1, k2, pu, ak, (phase = net_forward<A1, A2, PU, AK>(&cs, Pp, tmp, slot, want_grad ? 1 : 0, phase)));
     }
 
+    dbg_mark(&cs, 4);
+    // the lo-tile region Q is free between the forward and the reverse sweep: stage the program text and the
+    // per-point value / adjoint arrays there (shared memory instead of global + local memory)
+    const int n_instr = tm.n_instr;
+    DevInstr* sprog = reinterpret_cast<DevInstr*>(smem + args.off_Q);
+    float* sval = reinterpret_cast<float*>(smem + args.off_Q + 8192);
+    const bool prog_sm = (size_t)8192 + (size_t)2 * n_instr * kTcPts * 4 <= (size_t)(args.off_Q_bytes);
+    if (prog_sm) {
+      const int nw = n_instr * (int)(sizeof(DevInstr) / 4);
+      const int* src = reinterpret_cast<const int*>(tm.prog);
+      for (int i = tid; i < nw; i += kTcThreads) reinterpret_cast<int*>(sprog)[i] = __ldg(src + i);
+      __syncthreads();
+    }
     // ---- residual program, loss partial, tap adjoints (threads 0..127: one point each) -----------------------------------------
     if (tid < kTcPts) {
       float pbar[PINN_MAX_PARAMS];
 #pragma unroll
       for (int j = 0; j < PINN_MAX_PARAMS; ++j) pbar[j] = 0.f;
-      const float r = run_program<float, kTcPts>(tm, theta + P.param_off, ms.Xs, ms.taps, ms.tapbar, pbar, tid, want_grad);
+      float r;
+      if (prog_sm) {
+        r = run_program_t<float, kTcPts, true>(sprog, n_instr, theta + P.param_off, ms.Xs, ms.taps, ms.tapbar, pbar, tid,
+                                               want_grad, sval, sval + n_instr * kTcPts);
+      } else {
+        r = run_program<float, kTcPts>(tm, theta + P.param_off, ms.Xs, ms.taps, ms.tapbar, pbar, tid, want_grad);
+      }
       const float w = ms.qws[tid];
       double s = (double)w * (double)r * (double)r;
 #pragma unroll
@@ -927,9 +1012,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     }
     __syncthreads();
 
+    dbg_mark(&cs, 5);
     if (want_grad) {
       if (tid == 0) tc::bulk_wait0();             // stash writes of this tile are complete before reloads
       __syncthreads();
+      dbg_mark(&cs, 6);
       for (int slot = n_used - 1; slot >= 0; --slot) {
         const int k1 = tm.chan[slot].n1, k2 = tm.chan[slot].n2, pu = tm.chan[slot].pure;
         const int ak = args.net_ak[tm.used_net[slot]];
@@ -944,6 +1031,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
 
   tc::tc_fence_before();
   __syncthreads();
+  dbg_mark(&cs, 7);
+  if (tid == 0 && cs.dbg) cs.dbg[999] = cs.dbg_n;
   if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = ms.tsum[tid];
   if (warp == 0) tc::tmem_dealloc<512>(cs.tmem);
 }

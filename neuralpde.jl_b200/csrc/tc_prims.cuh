@@ -57,6 +57,18 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uin
                "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_store_u(void* gdst, uint32_t smem_src_addr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_src_addr), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_u(uint32_t smem_dst_addr, const void* gsrc, uint32_t bytes, uint32_t bar_addr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst_addr),
+               "l"(gsrc), "r"(bytes), "r"(bar_addr)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_u(uint32_t bar_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -118,6 +130,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// one lane of a fully active warp (warp-uniform code): lets the compiler keep the operands of
+// tcgen05.mma / cp.async.bulk in uniform registers instead of emitting a per-lane waterfall loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ uint64_t uni(uint64_t v) { return __shfl_sync(0xffffffffu, (unsigned long long)v, 0); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // ---- descriptors ---------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128-byte swizzle, sm_100 version field = 1

@@ -7,7 +7,10 @@
 namespace pinn {
 
 constexpr int kTcPts = 128;
-constexpr int kTcThreads = 256;
+#ifndef PINN_TC_THREADS
+#define PINN_TC_THREADS 512
+#endif
+constexpr int kTcThreads = PINN_TC_THREADS;
 constexpr int kTcMaxC = 5;
 constexpr int kTcMaxTaps = 6;
 constexpr int kTcMaxTL = 6;            // tensor (hidden->hidden) layers per network
@@ -41,7 +44,9 @@ struct TcArgs {
   int tile_begin, tile_end;
   int mode;               // 0 loss+grad, 1 loss only, 2 residual out
   float* resid_out;
+  long long* dbg;         // optional: 1000 x int64 phase timestamps of CTA 0 (pinn_debug_tc_timeline)
   int off_P, off_Q, off_misc;   // byte offsets into dynamic shared memory
+  int off_Q_bytes;              // size of the Q tile region
   TcNetSmem nets[PINN_MAX_NETS];
   int net_ak[PINN_MAX_NETS];   // 1: every hidden activation is tanh (fast path), 0: generic
   double seed[PINN_MAX_TERMS];

@@ -14,7 +14,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libpinn_b200.so")
+LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(HERE, "lib", "libpinn_b200.so")
 
 ABI_VERSION = 1
 MAX_IN = 8

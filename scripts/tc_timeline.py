@@ -1,0 +1,37 @@
+"""Phase timeline of one tile of the tcgen05 kernel (CTA 0), from in-kernel clock64() marks."""
+import ctypes as C, sys
+import numpy as np
+sys.path.insert(0, "."); sys.path.insert(0, "tests")
+import neuralpde_jl_b200 as npde
+from neuralpde_jl_b200 import configs
+mode = sys.argv[1] if len(sys.argv) > 1 else "tc_split"
+cfg = configs.config2()
+rep = npde.symbolic_discretize(cfg.pde_system, cfg.discretization(dtype=np.float32, mode=mode))
+eng = rep.engine
+lib = eng.lib
+lib.pinn_debug_tc_timeline.argtypes = [C.c_void_p, C.c_void_p]
+lib.pinn_debug_tc_timeline.restype = C.c_int
+th = rep.flat_init_params
+for _ in range(3):
+    eng.loss_grad_host(th, None, True)
+assert lib.pinn_debug_tc_timeline(eng._h, None) == 0
+eng.loss_grad_host(th, None, True)
+buf = np.zeros(1000, dtype=np.int64)
+assert lib.pinn_debug_tc_timeline(eng._h, buf.ctypes.data) == 0
+n = int(buf[999])
+ids = (buf[:n] >> 48).astype(int); clk = buf[:n] & ((1 << 48) - 1)
+names = {1: "start", 2: "setup done", 3: "tile loaded", 4: "fwd done", 5: "program done", 6: "stash drained", 7: "end",
+         10: "F enter", 11: "F l: tiles written+sync", 12: "F l: mma issued", 13: "F l: mma done", 14: "F l: stash read done+sync",
+         15: "F epilogues done", 16: "F exit", 20: "B enter", 21: "B l: start", 22: "B l: stash loaded", 23: "B g: sync",
+         24: "B g: refwd issued", 25: "B g: refwd done", 26: "B l: zbar written+sync", 27: "B l: dgrad+wgrad issued",
+         28: "B l: dgrad+wgrad done", 29: "B l0 start", 30: "B exit"}
+t0 = clk[0]
+prev = t0
+agg = {}
+for i, c in zip(ids, clk):
+    print("%8d  +%7d  %s" % (c - t0, c - prev, names.get(i, str(i))))
+    agg[names.get(i, str(i))] = agg.get(names.get(i, str(i)), 0) + (c - prev)
+    prev = c
+print("\n--- time attributed to the interval ENDING at each mark (cycles) ---")
+for k, v in sorted(agg.items(), key=lambda x: -x[1]):
+    print("%8d  %5.1f%%  %s" % (v, 100.0 * v / (clk[-1] - t0), k))
