@@ -67,23 +67,30 @@ __device__ __forceinline__ void act_eval_tc(int act, float z, float& a, float& d
 }
 __device__ __forceinline__ int act_kind(int act) { return act == PINN_ACT_TANH ? 1 : (act == PINN_ACT_SIGMOID ? 2 : 0); }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t x, uint32_t y) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+
 // store 4 consecutive columns (half of a 16-byte chunk) of a row into a swizzled tile; with `split`
 // also the bf16 residual v - bf16(v) into the lo tile
-__device__ __forceinline__ void store_half(uint8_t* tile_hi, uint8_t* tile_lo, int row, int col0, const float (&v)[4],
+__device__ __forceinline__ void store_half(uint32_t tile_hi, uint32_t tile_lo, int row, int col0, const float (&v)[4],
                                            bool split) {
 #ifdef PINN_EXP_NO_STS
   asm volatile("" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]));
   return;
 #endif
   const uint32_t off = tc::swz_chunk(row, col0 >> 3) + ((col0 & 4) << 1);
-  uint2 h;
-  h.x = tc::pack_bf16(v[0], v[1]); h.y = tc::pack_bf16(v[2], v[3]);
-  *reinterpret_cast<uint2*>(tile_hi + off) = h;
+  const uint32_t hx = tc::pack_bf16(v[0], v[1]), hy = tc::pack_bf16(v[2], v[3]);
+  sts_v2(tile_hi + off, hx, hy);
   if (split) {
-    uint2 l;
-    l.x = tc::pack_bf16(v[0] - __uint_as_float(h.x << 16), v[1] - __uint_as_float(h.x & 0xffff0000u));
-    l.y = tc::pack_bf16(v[2] - __uint_as_float(h.y << 16), v[3] - __uint_as_float(h.y & 0xffff0000u));
-    *reinterpret_cast<uint2*>(tile_lo + off) = l;
+    const uint32_t lx = tc::pack_bf16(v[0] - __uint_as_float(hx << 16), v[1] - __uint_as_float(hx & 0xffff0000u));
+    const uint32_t ly = tc::pack_bf16(v[2] - __uint_as_float(hy << 16), v[3] - __uint_as_float(hy & 0xffff0000u));
+    sts_v2(tile_lo + off, lx, ly);
   }
 }
 
@@ -231,17 +238,17 @@ __device__ __forceinline__ void load_pass(PassInfo<N1, N2>& pi, const DevNet& ne
   for (int s = 0; s < N2; ++s) { pi.ch.sa[s] = dc.s_a[s]; pi.ch.sb[s] = dc.s_b[s]; }
 }
 
-// first-layer pre-activations of neuron o (channel vector zz)
+// first-layer pre-activations of neuron o (channel vector zz); fpa = shared-memory address of the fp32 block
 template <int N1, int N2>
-__device__ __forceinline__ void first_layer_elem(const float* fp, const PassInfo<N1, N2>& pi, const float (&x)[PINN_MAX_IN],
+__device__ __forceinline__ void first_layer_elem(uint32_t fpa, const PassInfo<N1, N2>& pi, const float (&x)[PINN_MAX_IN],
                                                  int o, float* zz) {
-  float s = fp[FP_B1 + o];
+  float s = lds_f32(fpa + (FP_B1 + o) * 4);
 #pragma unroll
   for (int k = 0; k < PINN_MAX_IN; ++k)
-    if (k < pi.d_in) s = fmaf(fp[FP_W1 + o * 8 + k], x[k], s);
+    if (k < pi.d_in) s = fmaf(lds_f32(fpa + (FP_W1 + o * 8 + k) * 4), x[k], s);
   zz[0] = s;
 #pragma unroll
-  for (int j = 0; j < N1; ++j) zz[1 + j] = fp[FP_W1 + o * 8 + pi.dir1[j]];
+  for (int j = 0; j < N1; ++j) zz[1 + j] = lds_f32(fpa + (FP_W1 + o * 8 + pi.dir1[j]) * 4);
 #pragma unroll
   for (int j = 0; j < N2; ++j) zz[1 + N1 + j] = 0.f;
 }
@@ -279,10 +286,10 @@ __device__ __forceinline__ Tid tid_of() {
 // ---- granule loops (4 columns x all channels per step), specialised on the activation kind -------------
 // (inlined into the per-network passes; a noinline callee only gets the ABI scratch registers and spills)
 struct LoopCtx {
-  const float* fp;        // fp32 parameter block of the network (shared memory)
-  const float* bt;        // bias of the current tensor layer
-  uint8_t* tP;            // hi operand tiles
-  uint8_t* tQ;            // lo operand tiles (forward split)
+  uint32_t fp;            // shared-memory address of the network's fp32 parameter block
+  uint32_t bt;            // shared-memory address of the current tensor layer's bias
+  uint32_t tP;            // shared-memory address of the hi operand tiles
+  uint32_t tQ;            // shared-memory address of the lo operand tiles (forward split)
   float* gb;              // bias gradient of the current layer (CTA partial)
   float* gw;              // weight gradient of the first layer (CTA partial)
   uint32_t taddr;         // tmem base + lane quadrant
@@ -309,7 +316,7 @@ __device__ __forceinline__ void l0_fwd_loop(const LoopCtx lc, const PassInfo<N1,
 #pragma unroll
       for (int c = 0; c < C; ++c) h[c][i] = hv[c];
       if (lc.flag) {
-        const float wl = lc.fp[FP_WL + g * 4 + i];
+        const float wl = lds_f32(lc.fp + (FP_WL + g * 4 + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
       }
@@ -337,14 +344,14 @@ __device__ __forceinline__ void tl_fwd_loop(const LoopCtx lc, const Chan<N1, N2>
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float zz[C], hv[C];
-      zz[0] = z[0][i] + lc.bt[g * 4 + i];
+      zz[0] = z[0][i] + lds_f32(lc.bt + (g * 4 + i) * 4);
 #pragma unroll
       for (int c = 1; c < C; ++c) zz[c] = z[c][i];
       chain_fwd<N1, N2, PURE, AK>(lc.act, ch, zz, hv);
 #pragma unroll
       for (int c = 0; c < C; ++c) z[c][i] = hv[c];
       if (lc.flag) {
-        const float wl = lc.fp[FP_WL + g * 4 + i];
+        const float wl = lds_f32(lc.fp + (FP_WL + g * 4 + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
       }
@@ -380,7 +387,7 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
     if (lc.flag) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float wl = lc.fp[FP_WL + ocol + i];
+        const float wl = lds_f32(lc.fp + (FP_WL + ocol + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
       }
@@ -389,7 +396,7 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       float zz[C], hv[C], zv[C];
-      zz[0] = z[0][i] + lc.bt[ocol + i];
+      zz[0] = z[0][i] + lds_f32(lc.bt + (ocol + i) * 4);
 #pragma unroll
       for (int c = 1; c < C; ++c) zz[c] = z[c][i];
 #pragma unroll
@@ -428,7 +435,7 @@ __device__ __forceinline__ void l0_bwd_loop(const LoopCtx lc, const PassInfo<N1,
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float wl = lc.fp[FP_WL + g * 4 + i];
+        const float wl = lds_f32(lc.fp + (FP_WL + g * 4 + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
       }
@@ -509,8 +516,8 @@ __device__ __noinline__ uint32_t net_forward(CtaShared* cs, const DevProblem* Pp
     const int act0 = net.acts[0];
     const int ng = pi.n1w / 4;
     LoopCtx lc;
-    lc.fp = fp; lc.bt = fp; lc.tP = tP; lc.tQ = tQ; lc.gb = nullptr; lc.gw = nullptr; lc.taddr = tmem + t.lane_addr;
-    lc.act = act0; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
+    lc.fp = tc::smem_u32(fp); lc.bt = lc.fp; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = nullptr; lc.gw = nullptr;
+    lc.taddr = tmem + t.lane_addr; lc.act = act0; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
     lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
     l0_fwd_loop<N1, N2, PURE, AK>(lc, pi, x, u);
   }
@@ -565,7 +572,8 @@ __device__ __noinline__ uint32_t net_forward(CtaShared* cs, const DevProblem* Pp
     dbg_mark(cs, 14);
     const int ng = n_out / 4;
     LoopCtx lc;
-    lc.fp = fp; lc.bt = fp + FP_BT + (l - 1) * 64; lc.tP = tP; lc.tQ = tQ; lc.gb = nullptr; lc.gw = nullptr;
+    lc.fp = tc::smem_u32(fp); lc.bt = lc.fp + (FP_BT + (l - 1) * 64) * 4; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ);
+    lc.gb = nullptr; lc.gw = nullptr;
     lc.taddr = tmem + t.lane_addr; lc.act = act; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane;
     lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH); lc.c0 = 0; lc.flag = (l == TL) ? 1 : 0;
     tl_fwd_loop<N1, N2, PURE, AK>(lc, pi.ch, u);
@@ -734,7 +742,8 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
       dbg_mark(cs, 25);
       const int ng = gw_cols / 4;
       LoopCtx lc;
-      lc.fp = fp; lc.bt = bt; lc.tP = tP; lc.tQ = tQ; lc.gb = gb; lc.gw = nullptr; lc.taddr = tmem + t.lane_addr;
+      lc.fp = tc::smem_u32(fp); lc.bt = tc::smem_u32(bt); lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = gb; lc.gw = nullptr;
+      lc.taddr = tmem + t.lane_addr;
       lc.act = act; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
       lc.c0 = c0; lc.flag = (l == TL) ? 1 : 0;
       tl_bwd_loop<N1, N2, PURE, AK>(lc, pi.ch, ub);
@@ -796,7 +805,8 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
     float* gw0 = partial + net.w_off[0];
     const int ng = pi.n1w / 4;
     LoopCtx lc;
-    lc.fp = fp; lc.bt = fp; lc.tP = tP; lc.tQ = tQ; lc.gb = gb0; lc.gw = gw0; lc.taddr = tmem + t.lane_addr;
+    lc.fp = tc::smem_u32(fp); lc.bt = lc.fp; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = gb0; lc.gw = gw0;
+    lc.taddr = tmem + t.lane_addr;
     lc.act = act0; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
     lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
     l0_bwd_loop<N1, N2, PURE, AK>(lc, pi, x, ub);

@@ -276,6 +276,9 @@ class Engine:
         pts = np.asarray(pts, dtype=self.np_dtype)
         if pts.ndim != 2:
             raise ValueError("points must be a (d, n) matrix")
+        if pts.shape[0] != self.spec.terms[term].dim:
+            raise ValueError("term %d expects %d rows per point (coordinates + hoisted rows), got %d"
+                             % (term, self.spec.terms[term].dim, pts.shape[0]))
         buf = np.asfortranarray(pts)          # column-major: one point = d contiguous scalars
         flat = buf.ravel(order="F")
         w = None if weights is None else np.ascontiguousarray(weights, dtype=self.np_dtype)

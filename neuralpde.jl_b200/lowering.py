@@ -32,6 +32,64 @@ class LoweredTerm:
     prog: List[tuple]
     indvars: List[str]               # row i of the term's point matrix is this variable
     net_rows: List[Optional[List[int]]]
+    # coordinate-only subexpressions hoisted out of the per-step program: evaluated once per point set
+    # (float64, on the host) and appended as extra rows dim, dim+1, ... of the point matrix
+    extra_exprs: List[sp.Expr] = None
+
+    @property
+    def dim(self) -> int:
+        return len(self.indvars) + len(self.extra_exprs or [])
+
+    def augment(self, pts):
+        """(d, N) coordinates -> (d + n_extra, N) with the hoisted rows appended."""
+        import numpy as np
+        pts = np.asarray(pts)
+        if not self.extra_exprs:
+            return pts
+        if pts.shape[0] != len(self.indvars):
+            raise ValueError("expected %d coordinate rows, got %d" % (len(self.indvars), pts.shape[0]))
+        syms = [sp.Symbol(v, real=True) for v in self.indvars]
+        rows64 = [pts[i].astype(np.float64) for i in range(pts.shape[0])]
+        extra = []
+        for e in self.extra_exprs:
+            f = sp.lambdify(syms, e, "numpy")
+            extra.append(np.broadcast_to(np.asarray(f(*rows64), dtype=np.float64), rows64[0].shape))
+        return np.concatenate([pts, np.stack(extra).astype(pts.dtype)], axis=0)
+
+
+MAX_DIM = 8   # PINN_MAX_DIM
+
+
+def _hoist_coordinate_terms(expr, coord_names, blocked_names, extras, base_dim):
+    """Replace maximal coordinate-only subexpressions (no network tap, no trainable parameter) by fresh
+    symbols __c<i>; trivial ones (a bare symbol / number, or fewer than 2 operations) stay inline."""
+    def has_net(e):
+        return e.has(AppliedUndef) or e.has(sp.Derivative) or any(str(q) in blocked_names for q in e.free_symbols)
+
+    def rec(e):
+        if isinstance(e, (AppliedUndef, sp.Derivative, sp.Subs)):
+            return e
+        if not has_net(e):
+            names = {str(q) for q in e.free_symbols}
+            if names and names <= coord_names and not isinstance(e, sp.Symbol) and e.count_ops() >= 2 \
+                    and base_dim + len(extras) < MAX_DIM:
+                for i, old in enumerate(extras):
+                    if old == e:
+                        return sp.Symbol("__c%d" % i, real=True)
+                extras.append(e)
+                return sp.Symbol("__c%d" % (len(extras) - 1), real=True)
+            return e
+        if isinstance(e, (sp.Add, sp.Mul)):
+            pure = [a for a in e.args if not has_net(a)]
+            rest = [rec(a) for a in e.args if has_net(a)]
+            if pure:
+                rest.append(rec(e.func(*pure)))
+            return e.func(*rest, evaluate=False) if len(rest) > 1 else rest[0]
+        if e.args:
+            return e.func(*[rec(a) for a in e.args])
+        return e
+
+    return rec(sp.sympify(expr))
 
 
 class _Emitter:
@@ -79,6 +137,8 @@ class _Emitter:
             name = str(e)
             if name in self.rows:
                 return self._push("coord", a=self.rows.index(name))
+            if name.startswith("__c"):
+                return self._push("coord", a=len(self.rows) + int(name[3:]))
             if name in self.param_index:
                 return self._push("param", a=self.param_index[name])
             if name in self.param_values:
@@ -184,12 +244,18 @@ class _Emitter:
 
 
 def lower_equation(eq: Equation, vi: VarInfo, param_index: Optional[Dict[str, int]] = None,
-                   param_values: Optional[Dict[str, float]] = None) -> LoweredTerm:
+                   param_values: Optional[Dict[str, float]] = None, hoist: bool = False) -> LoweredTerm:
     """Equation -> taps + residual program (``lhs - rhs``)."""
     rows = eq_indvars(eq, vi)
     em = _Emitter(vi, rows, param_index or {}, param_values or {})
     lhs = expand_derivatives(eq.lhs)
     rhs = expand_derivatives(eq.rhs)
+    extras: List[sp.Expr] = []
+    if hoist:
+        # trainable parameters block hoisting; parameters with fixed defaults are substituted first
+        subs = {sp.Symbol(k, real=True): v for k, v in (param_values or {}).items()}
+        lhs = _hoist_coordinate_terms(lhs.subs(subs), set(rows), set(param_index or {}), extras, len(rows))
+        rhs = _hoist_coordinate_terms(rhs.subs(subs), set(rows), set(param_index or {}), extras, len(rows))
     a = em.emit(lhs)
     b = em.emit(rhs)
     em.prog.append(("sub", a, b, 0.0))      # not CSE'd: must be the last instruction
@@ -202,9 +268,9 @@ def lower_equation(eq: Equation, vi: VarInfo, param_index: Optional[Dict[str, in
             net_rows.append([rows.index(v) for v in ins])
         else:
             net_rows.append(None)
-    return LoweredTerm(em.taps, em.prog, rows, net_rows)
+    return LoweredTerm(em.taps, em.prog, rows, net_rows, extras)
 
 
 def term_spec(lt: LoweredTerm, reduction: int = REDUCE_MEAN, scale: float = 1.0) -> TermSpec:
-    return TermSpec(dim=len(lt.indvars), taps=lt.taps, prog=lt.prog, net_rows=lt.net_rows,
+    return TermSpec(dim=lt.dim, taps=lt.taps, prog=lt.prog, net_rows=lt.net_rows,
                     reduction=reduction, scale=scale)

@@ -316,8 +316,8 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
 
     # ---- lower equations (src/discretize.jl:505-539) -------------------------------------------------------
     try:
-        pde_terms = [lower_equation(e, vi, param_index, param_values) for e in eqs]
-        bc_terms = [lower_equation(e, vi, param_index, param_values) for e in bcs]
+        pde_terms = [lower_equation(e, vi, param_index, param_values, hoist=True) for e in eqs]
+        bc_terms = [lower_equation(e, vi, param_index, param_values, hoist=True) for e in bcs]
     except LoweringError as ex:
         raise ValueError(str(ex)) from ex
 
@@ -388,11 +388,17 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
     sampler_rng = np.random.default_rng(getattr(strategy, "seed", 0) + 7919 * rank)
     state = {"calls": 0}
 
-    def upload(i: int, pts: np.ndarray, w: Optional[np.ndarray] = None):
+    lowered = pde_terms + bc_terms
+
+    def augment(i: int, pts: np.ndarray) -> np.ndarray:
+        """append the hoisted coordinate-only rows of term i (float64 evaluation, then theta's eltype)"""
+        return lowered[i].augment(pts) if i < len(lowered) else pts
+
+    def upload(i: int, pts: np.ndarray, w: Optional[np.ndarray] = None, shard: bool = True):
         n = pts.shape[1]
-        lo, hi = shard_range(n, rank, world)
-        eng.set_points_host(i, pts[:, lo:hi], None if w is None else w[lo:hi])
-        if world > 1:
+        lo, hi = shard_range(n, rank, world) if shard else (0, n)
+        eng.set_points_host(i, augment(i, np.asarray(pts, dtype=dtype)[:, lo:hi]), None if w is None else w[lo:hi])
+        if world > 1 and shard:
             eng.set_global_count(i, n)
 
     for i in range(n_terms):
@@ -411,7 +417,7 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
             if isinstance(strategy, StochasticTraining):
                 lo, hi = shard_range(npts, rank, world)
                 pts = generate_random_points(hi - lo, b, dtype.type, sampler_rng)
-                eng.set_points_host(i, pts)
+                eng.set_points_host(i, augment(i, pts))
                 if world > 1:
                     eng.set_global_count(i, npts)
             else:
@@ -467,7 +473,7 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
             if pts.ndim == 1:
                 pts = pts.reshape(specs[i].dim, -1)
             old = point_sets[i]
-            eng.set_points_host(i, pts, None if quad_w[i] is None else np.ones(pts.shape[1], dtype=dtype))
+            eng.set_points_host(i, augment(i, pts), None if quad_w[i] is None else np.ones(pts.shape[1], dtype=dtype))
             r = eng.term_residual_host(i, np.asarray(theta, dtype=dtype), pts.shape[1])
             if old is not None:
                 upload(i, old, quad_w[i])
@@ -498,6 +504,14 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
     rep.point_sets = point_sets
     rep.quad_weights = quad_w
     rep.weights = weights
+
+    def set_points(i: int, pts, w=None, n_global: Optional[int] = None):
+        """Replace term i's point set ((d, N) coordinates; hoisted rows are appended here)."""
+        point_sets[i] = np.asarray(pts, dtype=dtype)
+        upload(i, point_sets[i], w, shard=False)
+        if n_global is not None:
+            eng.set_global_count(i, n_global)
+    rep.set_points = set_points
     return rep
 
 

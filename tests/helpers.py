@@ -52,6 +52,6 @@ def engine_eval_sets(cfg, dtype, sets, qw=None, mode="ffma", want_grad=True, the
     rep = npde.symbolic_discretize(cfg.pde_system, disc)
     th = rep.flat_init_params if theta is None else np.asarray(theta, dtype=dtype)
     for i, s in enumerate(sets):
-        rep.engine.set_points_host(i, s, None if qw is None else qw[i])
+        rep.set_points(i, s, None if qw is None else qw[i])
     total, terms, grad = rep.engine.loss_grad_host(th, None, want_grad)
     return rep, total, terms, grad

@@ -36,8 +36,7 @@ def test_sharded_sums_equal_full():
         cfg2, rr = _rep(dtype=np.float64)
         for i, s in enumerate(rep.point_sets[:5]):
             lo, hi = shard_range(s.shape[1], r, 2)
-            rr.engine.set_points_host(i, s[:, lo:hi])
-            rr.engine.set_global_count(i, s.shape[1])
+            rr.set_points(i, s[:, lo:hi], n_global=s.shape[1])
         _, t_r, g_r = rr.engine.loss_grad_host(th, None, True)
         acc_t += t_r; acc_g += g_r
     np.testing.assert_allclose(acc_t, terms, rtol=1e-12)
