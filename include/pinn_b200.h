@@ -208,6 +208,18 @@ int pinn_term_residual(pinn_handle h, int32_t term, const void* dev_theta, void*
                        void* stream);
 int pinn_term_residual_host(pinn_handle h, int32_t term, const void* host_theta, void* host_r);
 
+/* ---- device-resident optimizer loop ------------------------------------ */
+/* Adam (Optimisers.Adam semantics: m, v, bias-corrected step) fused into the gradient reduction, so a
+ * training iteration is two launches with no host round trip.  theta, m, v live in engine-owned device
+ * memory.  Valid while the point sets stay fixed (Grid / fixed-node quadrature / non-resampled sets);
+ * the reference's per-iteration host loop (Optimization.solve + Zygote) is what this replaces. */
+int pinn_adam_begin(pinn_handle h, const void* host_theta0, double lr, double beta1, double beta2, double eps);
+/* run n_steps iterations; host_total (nullable) receives the loss of the LAST evaluated theta,
+ * host_term_losses (nullable) its per-term losses.  Synchronises at the end. */
+int pinn_adam_iterate(pinn_handle h, int32_t n_steps, const double* host_weights, void* host_total,
+                      void* host_term_losses);
+int pinn_adam_theta(pinn_handle h, void* host_theta_out);
+
 /* ---- multi-GPU -------------------------------------------------------------------- */
 /* Attach an NCCL communicator built from a 128-byte ncclUniqueId that the caller
  * distributed (rank 0 obtains it from pinn_comm_unique_id). */

@@ -64,7 +64,7 @@ def _extra_units():
 def build(verbose: bool = False, force: bool = False, tc_threads: int = 0) -> str:
     """tc_threads != 0 builds an experimental variant library (libpinn_b200_t<N>.so) of the tcgen05 kernel."""
     global OBJDIR, LIB
-    if tc_threads and "build_x" not in OBJDIR:
+    if tc_threads and "build_x" not in OBJDIR and "build_d" not in OBJDIR:
         OBJDIR = os.path.join(HERE, "build_t%d" % tc_threads)
         LIB = os.path.join(LIBDIR, "libpinn_b200_t%d.so" % tc_threads)
         NVCC_FLAGS.append("-DPINN_TC_THREADS=%d" % tc_threads)
@@ -102,6 +102,10 @@ def build(verbose: bool = False, force: bool = False, tc_threads: int = 0) -> st
 
 if __name__ == "__main__":
     for a in sys.argv:
+        if a.startswith("-D"):      # experimental define: -DPINN_TC_GW=2 -> libpinn_b200_dPINN_TC_GW2.so
+            tag = a[2:].replace("=", "")
+            OBJDIR = os.path.join(HERE, "build_d" + tag); LIB = os.path.join(LIBDIR, "libpinn_b200_d%s.so" % tag)
+            NVCC_FLAGS.append(a)
         if a.startswith("-X"):      # timing experiments: -XNO_LDTM etc. -> libpinn_b200_x<name>.so
             OBJDIR = os.path.join(HERE, "build_x" + a[2:]); LIB = os.path.join(LIBDIR, "libpinn_b200_x%s.so" % a[2:])
             NVCC_FLAGS.append("-DPINN_EXP_" + a[2:])

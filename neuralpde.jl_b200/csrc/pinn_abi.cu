@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdarg.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -22,6 +23,9 @@ cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sum
                           int want_grad, cudaStream_t st);
 cudaError_t finish_launch(int dtype, const void* packed_terms, int n_terms, const ScaleW& scale_w, void* out_terms,
                           void* out_total, cudaStream_t st);
+cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+                               int n_terms, const ScaleW& sw, void* theta, void* m, void* v, double lr_t, double beta1,
+                               double beta2, double eps_t, void* out_terms, void* out_total, cudaStream_t st);
 }  // namespace pinn
 
 using namespace pinn;
@@ -119,6 +123,12 @@ struct pinn_engine {
   void* h_pin_in = nullptr;      // pinned theta
   void* h_pin_out = nullptr;     // pinned grad + losses
   cudaStream_t own_stream = nullptr;
+  // device-resident Adam state
+  void* adam_m = nullptr;
+  void* adam_v = nullptr;
+  double adam_lr = 1e-3, adam_b1 = 0.9, adam_b2 = 0.999, adam_eps = 1e-8;
+  long long adam_t = 0;
+  bool adam_ready = false;
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -479,7 +489,7 @@ int pinn_destroy(pinn_handle e) {
   cudaSetDevice(e->device);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   void* ptrs[] = {e->dprob, e->partial, e->term_sums, e->stash, e->gbufs, e->packed,
-                  e->d_theta, e->d_grad, e->d_out};
+                  e->d_theta, e->d_grad, e->d_out, e->adam_m, e->adam_v};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int t = 0; t < PINN_MAX_TERMS; ++t) {
     if (e->own_pts[t]) cudaFree(e->own_pts[t]);
@@ -730,6 +740,62 @@ int pinn_loss_grad_host(pinn_handle e, const void* host_theta, const double* hos
   if (host_grad) memcpy(host_grad, hout, tb);
   if (host_term_losses) memcpy(host_term_losses, hout + tb, (size_t)e->n_terms * e->es);
   memcpy(host_total, hout + tb + (size_t)e->n_terms * e->es, e->es);
+  return 0;
+}
+
+int pinn_adam_begin(pinn_handle e, const void* host_theta0, double lr, double beta1, double beta2, double eps) {
+  if (!e) return fail("pinn_adam_begin: null handle");
+  if (!host_theta0) return fail("pinn_adam_begin: null theta");
+  if (e->nranks > 1) return fail("pinn_adam_begin: the fused Adam loop is single-GPU (use pinn_loss_grad + your optimizer)");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t tb = (size_t)e->n_theta * e->es;
+  if (!e->adam_m) { if (dev_alloc(&e->adam_m, tb, e) || dev_alloc(&e->adam_v, tb, e)) return 1; }
+  CUDA_TRY(cudaMemsetAsync(e->adam_m, 0, tb, e->own_stream));
+  CUDA_TRY(cudaMemsetAsync(e->adam_v, 0, tb, e->own_stream));
+  CUDA_TRY(cudaMemcpyAsync(e->d_theta, host_theta0, tb, cudaMemcpyHostToDevice, e->own_stream));
+  CUDA_TRY(cudaStreamSynchronize(e->own_stream));
+  e->adam_lr = lr; e->adam_b1 = beta1; e->adam_b2 = beta2; e->adam_eps = eps; e->adam_t = 0; e->adam_ready = true;
+  return 0;
+}
+
+int pinn_adam_iterate(pinn_handle e, int32_t n_steps, const double* host_weights, void* host_total, void* host_term_losses) {
+  if (!e) return fail("pinn_adam_iterate: null handle");
+  if (!e->adam_ready) return fail("pinn_adam_iterate: call pinn_adam_begin first");
+  if (n_steps < 1) return fail("pinn_adam_iterate: n_steps must be >= 1");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (e->total_tiles <= 0) return fail("pinn_adam_iterate: no collocation points");
+  cudaStream_t st = e->own_stream;
+  char* dout = (char*)e->d_out;
+  const int grid = std::min(e->num_sms, e->total_tiles);
+  for (int it = 0; it < n_steps; ++it) {
+    FfmaArgs a;
+    memset(&a, 0, sizeof a);
+    fill_args(e, a, e->d_theta, 0);
+    ScaleW sw;
+    memset(&sw, 0, sizeof sw);
+    if (prepare_scales(e, host_weights, a, sw)) return 1;
+    if (launch_fused(e, a, grid, st)) return 1;
+    e->adam_t += 1;
+    const double c1 = 1.0 - pow(e->adam_b1, (double)e->adam_t), c2 = sqrt(1.0 - pow(e->adam_b2, (double)e->adam_t));
+    CUDA_TRY(reduce_adam_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, e->d_theta, e->adam_m,
+                                e->adam_v, e->adam_lr * c2 / c1, e->adam_b1, e->adam_b2, e->adam_eps * c2, dout,
+                                dout + (size_t)e->n_terms * e->es, st));
+    e->launches += 2;
+  }
+  char* hout = (char*)e->h_pin_out;
+  CUDA_TRY(cudaMemcpyAsync(hout, e->d_out, ((size_t)e->n_terms + 1) * e->es, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (host_term_losses) memcpy(host_term_losses, hout, (size_t)e->n_terms * e->es);
+  if (host_total) memcpy(host_total, hout + (size_t)e->n_terms * e->es, e->es);
+  return 0;
+}
+
+int pinn_adam_theta(pinn_handle e, void* host_theta_out) {
+  if (!e || !host_theta_out) return fail("pinn_adam_theta: null handle / output");
+  if (!e->adam_ready) return fail("pinn_adam_theta: call pinn_adam_begin first");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaMemcpyAsync(host_theta_out, e->d_theta, (size_t)e->n_theta * e->es, cudaMemcpyDeviceToHost, e->own_stream));
+  CUDA_TRY(cudaStreamSynchronize(e->own_stream));
   return 0;
 }
 

@@ -30,6 +30,14 @@ namespace pinn {
 
 // ---- small helpers ---------------------------------------------------------------------------------
 constexpr int kNH = kTcThreads / 128;   // warps per TMEM lane quadrant: each takes 1/kNH of the columns
+#ifndef PINN_TC_GW
+#define PINN_TC_GW 4
+#endif
+constexpr int GW = PINN_TC_GW;          // columns per epilogue granule (4 or 2)
+#ifndef PINN_TC_GWB
+#define PINN_TC_GWB 2
+#endif
+constexpr int GWB = PINN_TC_GWB;        // granule of the tensor-layer reverse epilogue (register-heaviest loop)
 
 template <int N>
 __device__ __forceinline__ float pick(const float* v, int idx) {
@@ -108,6 +116,26 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
   for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float (&v)[2]) {
+  uint32_t r[2];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+  v[0] = __uint_as_float(r[0]); v[1] = __uint_as_float(r[1]);
+}
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, float (&v)[4]) { tmem_ld4(taddr, v); }
+__device__ __forceinline__ void tmem_ldg(uint32_t taddr, float (&v)[2]) { tmem_ld2(taddr, v); }
+
+// 2-column variant of store_half
+__device__ __forceinline__ void store_half(uint32_t tile_hi, uint32_t tile_lo, int row, int col0, const float (&v)[2],
+                                           bool split) {
+  const uint32_t off = tc::swz_chunk(row, col0 >> 3) + ((col0 & 6) << 1);
+  const uint32_t hx = tc::pack_bf16(v[0], v[1]);
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_hi + off), "r"(hx) : "memory");
+  if (split) {
+    const uint32_t lx = tc::pack_bf16(v[0] - __uint_as_float(hx << 16), v[1] - __uint_as_float(hx & 0xffff0000u));
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile_lo + off), "r"(lx) : "memory");
+  }
+}
+
 // channel bookkeeping of one (term, network): value + N1 first + N2 second derivative channels.
 // PURE: second-derivative channel s is d2/dx_s^2 of first-derivative channel s (no index selects).
 template <int N1, int N2>
@@ -180,6 +208,20 @@ __device__ __forceinline__ float warp_reduce4(const float (&v)[4], int lane) {
   return r;
 }
 __device__ __forceinline__ int reduce4_elem(int lane) { return ((lane >> 4) & 1) * 2 + ((lane >> 3) & 1); }
+// 2 values: 5 shuffles; every lane gets the total of element e = (lane >> 4) & 1; lanes with (lane & 15) == 0 act
+__device__ __forceinline__ float warp_reduce2(const float (&v)[2], int lane) {
+  const bool up16 = (lane & 16) != 0;
+  float r = (up16 ? v[1] : v[0]) + __shfl_xor_sync(0xffffffffu, up16 ? v[0] : v[1], 16);
+  r += __shfl_xor_sync(0xffffffffu, r, 8);
+  r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+__device__ __forceinline__ float warp_reduceg(const float (&v)[4], int lane) { return warp_reduce4(v, lane); }
+__device__ __forceinline__ float warp_reduceg(const float (&v)[2], int lane) { return warp_reduce2(v, lane); }
+__device__ __forceinline__ int reduceg_elem(int lane) { return GW == 4 ? reduce4_elem(lane) : ((lane >> 4) & 1); }
+__device__ __forceinline__ bool reduceg_lead(int lane) { return GW == 4 ? ((lane & 7) == 0) : ((lane & 15) == 0); }
 
 // CTA-wide constants kept in shared memory so the per-network passes (separate functions) do not
 // drag a context struct through local memory
@@ -307,22 +349,22 @@ __device__ __forceinline__ void l0_fwd_loop(const LoopCtx lc, const PassInfo<N1,
   for (int c = 0; c < C; ++c) u[c] = up[c];
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
-    float h[C][4];
+    float h[C][GW];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GW; ++i) {
       float zz[C], hv[C];
-      first_layer_elem<N1, N2>(lc.fp, pi, x, g * 4 + i, zz);
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GW + i, zz);
       chain_fwd<N1, N2, PURE, AK>(lc.act, pi.ch, zz, hv);
 #pragma unroll
       for (int c = 0; c < C; ++c) h[c][i] = hv[c];
       if (lc.flag) {
-        const float wl = lds_f32(lc.fp + (FP_WL + g * 4 + i) * 4);
+        const float wl = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tQ + c * kTileBytes, lc.p, g * 4, h[c], lc.split != 0);
+    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tQ + c * kTileBytes, lc.p, g * GW, h[c], lc.split != 0);
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) up[c] = u[c];
@@ -337,27 +379,27 @@ __device__ __forceinline__ void tl_fwd_loop(const LoopCtx lc, const Chan<N1, N2>
   for (int c = 0; c < C; ++c) u[c] = up[c];
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
-    float z[C][4];
+    float z[C][GW];
 #pragma unroll
-    for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_X + c * 64 + g * 4, z[c]);
+    for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + g * GW, z[c]);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GW; ++i) {
       float zz[C], hv[C];
-      zz[0] = z[0][i] + lds_f32(lc.bt + (g * 4 + i) * 4);
+      zz[0] = z[0][i] + lds_f32(lc.bt + (g * GW + i) * 4);
 #pragma unroll
       for (int c = 1; c < C; ++c) zz[c] = z[c][i];
       chain_fwd<N1, N2, PURE, AK>(lc.act, ch, zz, hv);
 #pragma unroll
       for (int c = 0; c < C; ++c) z[c][i] = hv[c];
       if (lc.flag) {
-        const float wl = lds_f32(lc.fp + (FP_WL + g * 4 + i) * 4);
+        const float wl = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
       }
     }
 #pragma unroll
-    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tQ + c * kTileBytes, lc.p, g * 4, z[c], lc.split != 0);
+    for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tQ + c * kTileBytes, lc.p, g * GW, z[c], lc.split != 0);
   }
 #pragma unroll
   for (int c = 0; c < C; ++c) up[c] = u[c];
@@ -371,30 +413,30 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
-  const int re = reduce4_elem(lc.lane);
-  const bool rlead = (lc.lane & 7) == 0;
+  const int re = GWB == 4 ? reduce4_elem(lc.lane) : ((lc.lane >> 4) & 1);
+  const bool rlead = GWB == 4 ? ((lc.lane & 7) == 0) : ((lc.lane & 15) == 0);
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
-    const int ocol = lc.c0 + g * 4;
-    float z[C][4], hb[C][4];
+    const int ocol = lc.c0 + g * GWB;
+    float z[C][GWB], hb[C][GWB];
 #pragma unroll
-    for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_Y + c * 32 + g * 4, z[c]);
+    for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_Y + c * 32 + g * GWB, z[c]);
     if (!lc.flag) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_X + c * 64 + ocol, hb[c]);
+      for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + ocol, hb[c]);
     }
     tc::tmem_ld_wait();
     if (lc.flag) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
+      for (int i = 0; i < GWB; ++i) {
         const float wl = lds_f32(lc.fp + (FP_WL + ocol + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
       }
     }
-    float zb0[4];
+    float zb0[GWB];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GWB; ++i) {
       float zz[C], hv[C], zv[C];
       zz[0] = z[0][i] + lds_f32(lc.bt + (ocol + i) * 4);
 #pragma unroll
@@ -406,7 +448,7 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
       for (int c = 0; c < C; ++c) hb[c][i] = zv[c];
       zb0[i] = zv[0];
     }
-    const float bs = warp_reduce4(zb0, lc.lane);
+    const float bs = warp_reduceg(zb0, lc.lane);
     if (rlead) atomicAdd(lc.gb + ocol + re, bs);
 #pragma unroll
     for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tP, lc.p, ocol, hb[c], false);
@@ -422,29 +464,29 @@ __device__ __forceinline__ void l0_bwd_loop(const LoopCtx lc, const PassInfo<N1,
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = xp[k];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
-  const int re = reduce4_elem(lc.lane);
-  const bool rlead = (lc.lane & 7) == 0;
+  const int re = reduceg_elem(lc.lane);
+  const bool rlead = reduceg_lead(lc.lane);
   const int n1w = pi.n1w;
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
-    float hb[C][4];
+    float hb[C][GW];
     if (!lc.flag) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + TM_X + c * 64 + g * 4, hb[c]);
+      for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + g * GW, hb[c]);
       tc::tmem_ld_wait();
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float wl = lds_f32(lc.fp + (FP_WL + g * 4 + i) * 4);
+      for (int i = 0; i < GW; ++i) {
+        const float wl = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4);
 #pragma unroll
         for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
       }
     }
-    float zv0[4], zvd[N1 > 0 ? N1 : 1][4];
+    float zv0[GW], zvd[N1 > 0 ? N1 : 1][GW];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < GW; ++i) {
       float zz[C], hv[C], zv[C];
-      first_layer_elem<N1, N2>(lc.fp, pi, x, g * 4 + i, zz);
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GW + i, zz);
 #pragma unroll
       for (int c = 0; c < C; ++c) hv[c] = hb[c][i];
       chain_bwd<N1, N2, PURE, AK>(lc.act, pi.ch, zz, hv, zv);
@@ -453,21 +495,21 @@ __device__ __forceinline__ void l0_bwd_loop(const LoopCtx lc, const PassInfo<N1,
       for (int jd = 0; jd < N1; ++jd) zvd[jd][i] = zv[1 + jd];
     }
     // Wbar_0[o][k] = sum_p zbar_0 x_k + zbar_(channel of direction k);  bbar_0[o] = sum_p zbar_0
-    const float bs = warp_reduce4(zv0, lc.lane);
-    if (rlead) atomicAdd(lc.gb + g * 4 + re, bs);
+    const float bs = warp_reduceg(zv0, lc.lane);
+    if (rlead) atomicAdd(lc.gb + g * GW + re, bs);
 #pragma unroll
     for (int k = 0; k < PINN_MAX_IN; ++k) {
       if (k < pi.d_in) {
-        float gk[4];
+        float gk[GW];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < GW; ++i) {
           float gg = zv0[i] * x[k];
 #pragma unroll
           for (int jd = 0; jd < N1; ++jd) gg += (pi.dir1[jd] == k) ? zvd[jd][i] : 0.f;
           gk[i] = gg;
         }
-        const float gs = warp_reduce4(gk, lc.lane);
-        if (rlead) atomicAdd(lc.gw + g * 4 + re + (long long)n1w * k, gs);
+        const float gs = warp_reduceg(gk, lc.lane);
+        if (rlead) atomicAdd(lc.gw + g * GW + re + (long long)n1w * k, gs);
       }
     }
   }
@@ -514,7 +556,7 @@ __device__ __noinline__ uint32_t net_forward(CtaShared* cs, const DevProblem* Pp
   {
     // ---- layer 0 on the CUDA cores ------------------------------------------------------------------
     const int act0 = net.acts[0];
-    const int ng = pi.n1w / 4;
+    const int ng = pi.n1w / GW;
     LoopCtx lc;
     lc.fp = tc::smem_u32(fp); lc.bt = lc.fp; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = nullptr; lc.gw = nullptr;
     lc.taddr = tmem + t.lane_addr; lc.act = act0; lc.split = split ? 1 : 0; lc.p = p; lc.lane = t.lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
@@ -570,7 +612,7 @@ __device__ __noinline__ uint32_t net_forward(CtaShared* cs, const DevProblem* Pp
     }
     __syncthreads();
     dbg_mark(cs, 14);
-    const int ng = n_out / 4;
+    const int ng = n_out / GW;
     LoopCtx lc;
     lc.fp = tc::smem_u32(fp); lc.bt = lc.fp + (FP_BT + (l - 1) * 64) * 4; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ);
     lc.gb = nullptr; lc.gw = nullptr;
@@ -740,7 +782,7 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
       wait_bar(ms.bar_mma, mma_phase);
       tc::tc_fence_after();
       dbg_mark(cs, 25);
-      const int ng = gw_cols / 4;
+      const int ng = gw_cols / GWB;
       LoopCtx lc;
       lc.fp = tc::smem_u32(fp); lc.bt = tc::smem_u32(bt); lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = gb; lc.gw = nullptr;
       lc.taddr = tmem + t.lane_addr;
@@ -803,7 +845,7 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
     const int act0 = net.acts[0];
     float* gb0 = partial + net.b_off[0];
     float* gw0 = partial + net.w_off[0];
-    const int ng = pi.n1w / 4;
+    const int ng = pi.n1w / GW;
     LoopCtx lc;
     lc.fp = tc::smem_u32(fp); lc.bt = lc.fp; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = gb0; lc.gw = gw0;
     lc.taddr = tmem + t.lane_addr;

@@ -35,7 +35,7 @@ EXPORTS = [
     "pinn_set_points_host", "pinn_set_global_count", "pinn_loss_grad", "pinn_loss_grad_host",
     "pinn_term_residual", "pinn_term_residual_host", "pinn_comm_unique_id", "pinn_comm_init",
     "pinn_launch_count", "pinn_set_timing", "pinn_last_kernel_ms", "pinn_workspace_bytes",
-    "pinn_flops_per_eval",
+    "pinn_flops_per_eval", "pinn_adam_begin", "pinn_adam_iterate", "pinn_adam_theta",
 ]
 
 
@@ -162,6 +162,12 @@ def load_library():
     lib.pinn_workspace_bytes.restype = i64
     lib.pinn_flops_per_eval.argtypes = [vp]
     lib.pinn_flops_per_eval.restype = dbl
+    lib.pinn_adam_begin.argtypes = [vp, vp, dbl, dbl, dbl, dbl]
+    lib.pinn_adam_begin.restype = C.c_int
+    lib.pinn_adam_iterate.argtypes = [vp, i32, C.POINTER(dbl), vp, vp]
+    lib.pinn_adam_iterate.restype = C.c_int
+    lib.pinn_adam_theta.argtypes = [vp, vp]
+    lib.pinn_adam_theta.restype = C.c_int
     _lib = lib
     return lib
 
@@ -323,6 +329,25 @@ class Engine:
 
     def term_residual_device(self, term: int, dev_theta, dev_r, stream: int = 0):
         _check(self.lib.pinn_term_residual(self._h, term, _ptr(dev_theta), _ptr(dev_r), C.c_void_p(stream)))
+
+    # -- device-resident Adam loop ----------------------------------------------------------------------
+    def adam_begin(self, theta0: np.ndarray, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8):
+        th = np.ascontiguousarray(theta0, dtype=self.np_dtype)
+        _check(self.lib.pinn_adam_begin(self._h, _ptr(th), float(lr), float(beta1), float(beta2), float(eps)))
+
+    def adam_iterate(self, n_steps: int, weights=None):
+        """Run n_steps fused iterations on the device; returns (loss, term_losses) of the last evaluated theta."""
+        terms = np.empty(self.n_terms, dtype=self.np_dtype)
+        total = np.empty(1, dtype=self.np_dtype)
+        w = self._weights(weights)
+        wp = w.ctypes.data_as(C.POINTER(C.c_double)) if w is not None else None
+        _check(self.lib.pinn_adam_iterate(self._h, int(n_steps), wp, _ptr(total), _ptr(terms)))
+        return float(total[0]), terms
+
+    def adam_theta(self) -> np.ndarray:
+        th = np.empty(self.n_theta, dtype=self.np_dtype)
+        _check(self.lib.pinn_adam_theta(self._h, _ptr(th)))
+        return th
 
     # -- multi-GPU --------------------------------------------------------------------------------
     @staticmethod

@@ -555,9 +555,30 @@ class Solution:
     iterations: int
 
 
-def solve(prob: OptimizationProblem, opt: Adam, maxiters: int = 100, callback: Optional[Callable] = None) -> Solution:
-    """Minimal stand-in for ``Optimization.solve(prob, Adam(lr); maxiters, callback)``: a host Adam
-    loop that calls the engine's loss+gradient once per iteration."""
+def solve(prob: OptimizationProblem, opt: Adam, maxiters: int = 100, callback: Optional[Callable] = None,
+          device_loop: bool = False, chunk: int = 50) -> Solution:
+    """Minimal stand-in for ``Optimization.solve(prob, Adam(lr); maxiters, callback)``.
+
+    Default: a host Adam loop that calls the engine's loss+gradient once per iteration.
+    ``device_loop=True`` (fixed point sets only): theta, m, v stay on the device and the Adam update is
+    fused into the gradient reduction (pinn_adam_iterate); the callback sees the loss every `chunk` steps."""
+    rep = prob.representation
+    if device_loop:
+        if rep is None or isinstance(rep.strategy, StochasticTraining) or \
+                (isinstance(rep.strategy, QuasiRandomTraining) and rep.strategy.resampling):
+            raise ValueError("device_loop needs fixed point sets (Grid, Quadrature or non-resampled QuasiRandom)")
+        eng = rep.engine
+        eng.adam_begin(prob.u0, opt.lr, opt.beta1, opt.beta2, opt.eps)
+        done, obj = 0, float("nan")
+        w = np.concatenate([rep.weights["pde"], rep.weights["bc"]] +
+                           ([rep.weights["add"]] if rep.additional_loss is not None else []))
+        while done < maxiters:
+            n = min(chunk, maxiters - done)
+            obj, _ = eng.adam_iterate(n, w)
+            done += n
+            if callback is not None and callback({"iter": done, "u": None}, obj):
+                break
+        return Solution(eng.adam_theta(), obj, done)
     u = prob.u0.astype(np.float64).copy()
     m, v = np.zeros_like(u), np.zeros_like(u)
     obj = float("nan")

@@ -70,3 +70,29 @@ def test_phi_prediction_and_adam_step():
     import torch
     ref = R.phi(torch.tensor([[0.25, 0.5], [0.75, 0.5]]), torch.tensor(res.u.astype(np.float64)), *cfg.chain_specs()[0]).numpy()
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-6)
+
+
+def test_device_adam_loop_matches_host_adam():
+    """pinn_adam_iterate (Adam fused into the gradient reduction, theta resident on the device) follows the same
+    trajectory as the host Adam loop that calls pinn_loss_grad every iteration."""
+    cfg = configs.config2(n=16, width=16, hidden=2)
+    prob_h = npde.discretize(cfg.pde_system, cfg.discretization(dtype=np.float64))
+    prob_d = npde.discretize(cfg.pde_system, cfg.discretization(dtype=np.float64))
+    res_h = npde.solve(prob_h, npde.Adam(0.01), maxiters=7)
+    res_d = npde.solve(prob_d, npde.Adam(0.01), maxiters=7, device_loop=True, chunk=3)
+    assert res_d.iterations == 7
+    np.testing.assert_allclose(res_d.u, res_h.u, rtol=1e-9, atol=1e-12)
+    assert abs(res_d.objective - res_h.objective) <= 1e-9 * abs(res_h.objective)
+    # fp32 + tensor-core mode: a few steps reduce the loss
+    cfg2 = configs.config2(n=32, width=32, hidden=3)
+    prob_t = npde.discretize(cfg2.pde_system, cfg2.discretization(dtype=np.float32, mode="tc_split"))
+    l0 = prob_t.f.f(prob_t.u0, None)
+    res_t = npde.solve(prob_t, npde.Adam(0.003), maxiters=40, device_loop=True, chunk=20)
+    assert np.isfinite(res_t.objective) and res_t.objective < l0
+
+
+def test_device_loop_rejects_resampled_sets():
+    cfg = configs.config3(points=256, bcs_points=32, width=16, hidden=2)
+    prob = npde.discretize(cfg.pde_system, cfg.discretization(dtype=np.float32))
+    with pytest.raises(ValueError, match="fixed point sets"):
+        npde.solve(prob, npde.Adam(0.01), maxiters=2, device_loop=True)
