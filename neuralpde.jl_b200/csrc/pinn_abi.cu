@@ -861,17 +861,18 @@ int pinn_comm_init(pinn_handle e, const void* uid, int32_t rank, int32_t nranks)
 }
 
 // diagnostic (not part of the drop-in ABI): enable phase timestamps of CTA 0 in the tcgen05 kernel and
-// read them back (1000 x int64: id << 48 | clock); host_out == NULL only enables.
+// read them back (2000 x int64: [0,1000) phase marks id << 48 | clock, [1000,2000) per-CTA
+// {globaltimer start, end, cycles, smid}); host_out == NULL only enables.
 int pinn_debug_tc_timeline(pinn_handle e, long long* host_out) {
   if (!e) return fail("pinn_debug_tc_timeline: null handle");
   CUDA_TRY(cudaSetDevice(e->device));
   if (!e->tc_dbg) {
-    CUDA_TRY(cudaMalloc((void**)&e->tc_dbg, 1000 * sizeof(long long)));
-    CUDA_TRY(cudaMemset(e->tc_dbg, 0, 1000 * sizeof(long long)));
+    CUDA_TRY(cudaMalloc((void**)&e->tc_dbg, 2000 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(e->tc_dbg, 0, 2000 * sizeof(long long)));
   }
   if (host_out) {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(host_out, e->tc_dbg, 1000 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(host_out, e->tc_dbg, 2000 * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   return 0;
 }

@@ -136,6 +136,32 @@ __device__ __forceinline__ void store_half(uint32_t tile_hi, uint32_t tile_lo, i
   }
 }
 
+// ---- packed fp32x2 arithmetic (Blackwell FFMA2 / FMUL2 / FADD2): two columns per instruction ---------------
+struct P2 { float2 v; };
+__device__ __forceinline__ P2 mk2(float a, float b) { P2 r; r.v = make_float2(a, b); return r; }
+__device__ __forceinline__ P2 splat2(float a) { return mk2(a, a); }
+__device__ __forceinline__ P2 operator*(P2 a, P2 b) { P2 r; r.v = __fmul2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ P2 operator+(P2 a, P2 b) { P2 r; r.v = __fadd2_rn(a.v, b.v); return r; }
+__device__ __forceinline__ P2 vfma(P2 a, P2 b, P2 c) { P2 r; r.v = __ffma2_rn(a.v, b.v, c.v); return r; }
+__device__ __forceinline__ float vfma(float a, float b, float c) { return fmaf(a, b, c); }
+template <typename T> __device__ __forceinline__ T vsplat(float x);
+template <> __device__ __forceinline__ float vsplat<float>(float x) { return x; }
+template <> __device__ __forceinline__ P2 vsplat<P2>(float x) { return splat2(x); }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// tanh and its first three derivatives for two columns at once
+__device__ __forceinline__ void tanh_eval2(P2 z, P2& a, P2& d1, P2& d2, P2& d3) {
+  const P2 zz = z * splat2(2.8853900817779268f);                 // 2 * log2(e)
+  const P2 den = mk2(ex2_approx(zz.v.x), ex2_approx(zz.v.y)) + splat2(1.f);
+  const P2 r = mk2(rcp_approx(den.v.x), rcp_approx(den.v.y));
+  const P2 t = vfma(r, splat2(-2.f), splat2(1.f));
+  const P2 s = vfma(t * splat2(-1.f), t, splat2(1.f));
+  a = t; d1 = s;
+  d2 = (t * s) * splat2(-2.f);
+  d3 = s * vfma(t * splat2(6.f), t, splat2(-2.f));
+}
+
 // channel bookkeeping of one (term, network): value + N1 first + N2 second derivative channels.
 // PURE: second-derivative channel s is d2/dx_s^2 of first-derivative channel s (no index selects).
 template <int N1, int N2>
@@ -143,48 +169,77 @@ struct Chan {
   int sa[N2 > 0 ? N2 : 1], sb[N2 > 0 ? N2 : 1];
 };
 
-// post-activation channels from pre-activation channels (z[0] value, z[1..N1], z[1+N1..])
-template <int N1, int N2, bool PURE, int AK>
-__device__ __forceinline__ void chain_fwd(int act, const Chan<N1, N2>& ch, const float* z, float* h) {
+template <typename T, int N>
+__device__ __forceinline__ T pickT(const T* v, int idx) {
+  T r = v[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) r = (idx == i) ? v[i] : r;
+  return r;
+}
+
+// activation dispatch on the value type: packed tanh for P2, scalar evaluators otherwise
+template <int AK>
+__device__ __forceinline__ void act_any(int act, float z, float& a, float& d1, float& d2, float& d3) {
+  act_eval_tc<AK>(act, z, a, d1, d2, d3);
+}
+template <int AK>
+__device__ __forceinline__ void act_any(int act, P2 z, P2& a, P2& d1, P2& d2, P2& d3) {
+  if (AK == 1) {
+    tanh_eval2(z, a, d1, d2, d3);
+  } else {
+    float ax, d1x, d2x, d3x, ay, d1y, d2y, d3y;
+    act_eval_tc<AK>(act, z.v.x, ax, d1x, d2x, d3x);
+    act_eval_tc<AK>(act, z.v.y, ay, d1y, d2y, d3y);
+    a = mk2(ax, ay); d1 = mk2(d1x, d1y); d2 = mk2(d2x, d2y); d3 = mk2(d3x, d3y);
+  }
+}
+
+// post-activation channels from pre-activation channels (z[0] value, z[1..N1], z[1+N1..]); T = float or P2
+template <int N1, int N2, bool PURE, int AK, typename T>
+__device__ __forceinline__ void chain_fwd(int act, const Chan<N1, N2>& ch, const T* z, T* h) {
   constexpr int M1 = (N1 > 0) ? N1 : 1;
-  float a, d1, d2, d3;
-  act_eval_tc<AK>(act, z[0], a, d1, d2, d3);
+  T a, d1, d2, d3;
+  act_any<AK>(act, z[0], a, d1, d2, d3);
   h[0] = a;
 #pragma unroll
   for (int i = 0; i < N1; ++i) h[1 + i] = d1 * z[1 + i];
 #pragma unroll
   for (int s = 0; s < N2; ++s) {
-    const float za = PURE ? z[1 + (s < N1 ? s : 0)] : pick<M1>(z + 1, ch.sa[s]);
-    const float zb = PURE ? za : pick<M1>(z + 1, ch.sb[s]);
-    h[1 + N1 + s] = fmaf(d1, z[1 + N1 + s], d2 * za * zb);
+    const T za = PURE ? z[1 + (s < N1 ? s : 0)] : pickT<T, M1>(z + 1, ch.sa[s]);
+    const T zb = PURE ? za : pickT<T, M1>(z + 1, ch.sb[s]);
+    h[1 + N1 + s] = vfma(d1, z[1 + N1 + s], d2 * za * zb);
   }
 }
 
-// adjoints of pre-activations from adjoints of post-activations
-template <int N1, int N2, bool PURE, int AK>
-__device__ __forceinline__ void chain_bwd(int act, const Chan<N1, N2>& ch, const float* z, const float* hb, float* zb) {
+// adjoints of pre-activations from adjoints of post-activations; T = float or P2
+template <int N1, int N2, bool PURE, int AK, typename T>
+__device__ __forceinline__ void chain_bwd(int act, const Chan<N1, N2>& ch, const T* z, const T* hb, T* zb) {
   constexpr int M1 = (N1 > 0) ? N1 : 1;
-  float a, d1, d2, d3;
-  act_eval_tc<AK>(act, z[0], a, d1, d2, d3);
-  float acc0 = d1 * hb[0];
+  T a, d1, d2, d3;
+  act_any<AK>(act, z[0], a, d1, d2, d3);
+  T acc0 = d1 * hb[0];
 #pragma unroll
   for (int i = 0; i < N1; ++i) {
-    acc0 = fmaf(d2 * z[1 + i], hb[1 + i], acc0);
+    acc0 = vfma(d2 * z[1 + i], hb[1 + i], acc0);
     zb[1 + i] = d1 * hb[1 + i];
   }
 #pragma unroll
   for (int s = 0; s < N2; ++s) {
-    const float g = hb[1 + N1 + s];
+    const T g = hb[1 + N1 + s];
     if (PURE) {
       const int i = s < N1 ? s : 0;
-      const float za = z[1 + i];
-      acc0 = fmaf(fmaf(d2, z[1 + N1 + s], d3 * za * za), g, acc0);
-      zb[1 + i] = fmaf(2.f * d2 * za, g, zb[1 + i]);
+      const T za = z[1 + i];
+      acc0 = vfma(vfma(d2, z[1 + N1 + s], d3 * za * za), g, acc0);
+      zb[1 + i] = vfma((d2 * za) * vsplat<T>(2.f), g, zb[1 + i]);
     } else {
-      const float za = pick<M1>(z + 1, ch.sa[s]), zbb = pick<M1>(z + 1, ch.sb[s]);
-      acc0 = fmaf(fmaf(d2, z[1 + N1 + s], d3 * za * zbb), g, acc0);
-      add_at<M1>(zb + 1, ch.sa[s], d2 * zbb * g);
-      add_at<M1>(zb + 1, ch.sb[s], d2 * za * g);
+      const T za = pickT<T, M1>(z + 1, ch.sa[s]), zbb = pickT<T, M1>(z + 1, ch.sb[s]);
+      acc0 = vfma(vfma(d2, z[1 + N1 + s], d3 * za * zbb), g, acc0);
+      const T ga = d2 * zbb * g, gb2 = d2 * za * g;
+#pragma unroll
+      for (int i = 0; i < M1; ++i) {
+        if (ch.sa[s] == i) zb[1 + i] = zb[1 + i] + ga;
+        if (ch.sb[s] == i) zb[1 + i] = zb[1 + i] + gb2;
+      }
     }
     zb[1 + N1 + s] = d1 * g;
   }
@@ -351,16 +406,20 @@ __device__ __forceinline__ void l0_fwd_loop(const LoopCtx lc, const PassInfo<N1,
   for (int g = lc.g0; g < lc.g1; ++g) {
     float h[C][GW];
 #pragma unroll
-    for (int i = 0; i < GW; ++i) {
-      float zz[C], hv[C];
-      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GW + i, zz);
-      chain_fwd<N1, N2, PURE, AK>(lc.act, pi.ch, zz, hv);
+    for (int i = 0; i < GW; i += 2) {
+      float za[C], zb2[C];
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GW + i, za);
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GW + i + 1, zb2);
+      P2 zz[C], hv[C];
 #pragma unroll
-      for (int c = 0; c < C; ++c) h[c][i] = hv[c];
+      for (int c = 0; c < C; ++c) zz[c] = mk2(za[c], zb2[c]);
+      chain_fwd<N1, N2, PURE, AK, P2>(lc.act, pi.ch, zz, hv);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { h[c][i] = hv[c].v.x; h[c][i + 1] = hv[c].v.y; }
       if (lc.flag) {
-        const float wl = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4);
+        const float w0 = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4), w1 = lds_f32(lc.fp + (FP_WL + g * GW + i + 1) * 4);
 #pragma unroll
-        for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
+        for (int c = 0; c < C; ++c) u[c] = fmaf(w1, hv[c].v.y, fmaf(w0, hv[c].v.x, u[c]));
       }
     }
 #pragma unroll
@@ -384,18 +443,18 @@ __device__ __forceinline__ void tl_fwd_loop(const LoopCtx lc, const Chan<N1, N2>
     for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + g * GW, z[c]);
     tc::tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < GW; ++i) {
-      float zz[C], hv[C];
-      zz[0] = z[0][i] + lds_f32(lc.bt + (g * GW + i) * 4);
+    for (int i = 0; i < GW; i += 2) {
+      P2 zz[C], hv[C];
+      zz[0] = mk2(z[0][i] + lds_f32(lc.bt + (g * GW + i) * 4), z[0][i + 1] + lds_f32(lc.bt + (g * GW + i + 1) * 4));
 #pragma unroll
-      for (int c = 1; c < C; ++c) zz[c] = z[c][i];
-      chain_fwd<N1, N2, PURE, AK>(lc.act, ch, zz, hv);
+      for (int c = 1; c < C; ++c) zz[c] = mk2(z[c][i], z[c][i + 1]);
+      chain_fwd<N1, N2, PURE, AK, P2>(lc.act, ch, zz, hv);
 #pragma unroll
-      for (int c = 0; c < C; ++c) z[c][i] = hv[c];
+      for (int c = 0; c < C; ++c) { z[c][i] = hv[c].v.x; z[c][i + 1] = hv[c].v.y; }
       if (lc.flag) {
-        const float wl = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4);
+        const float w0 = lds_f32(lc.fp + (FP_WL + g * GW + i) * 4), w1 = lds_f32(lc.fp + (FP_WL + g * GW + i + 1) * 4);
 #pragma unroll
-        for (int c = 0; c < C; ++c) u[c] = fmaf(wl, hv[c], u[c]);
+        for (int c = 0; c < C; ++c) u[c] = fmaf(w1, hv[c].v.y, fmaf(w0, hv[c].v.x, u[c]));
       }
     }
 #pragma unroll
@@ -436,17 +495,17 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
     }
     float zb0[GWB];
 #pragma unroll
-    for (int i = 0; i < GWB; ++i) {
-      float zz[C], hv[C], zv[C];
-      zz[0] = z[0][i] + lds_f32(lc.bt + (ocol + i) * 4);
+    for (int i = 0; i < GWB; i += 2) {
+      P2 zz[C], hv[C], zv[C];
+      zz[0] = mk2(z[0][i] + lds_f32(lc.bt + (ocol + i) * 4), z[0][i + 1] + lds_f32(lc.bt + (ocol + i + 1) * 4));
 #pragma unroll
-      for (int c = 1; c < C; ++c) zz[c] = z[c][i];
+      for (int c = 1; c < C; ++c) zz[c] = mk2(z[c][i], z[c][i + 1]);
 #pragma unroll
-      for (int c = 0; c < C; ++c) hv[c] = hb[c][i];
-      chain_bwd<N1, N2, PURE, AK>(lc.act, ch, zz, hv, zv);
+      for (int c = 0; c < C; ++c) hv[c] = mk2(hb[c][i], hb[c][i + 1]);
+      chain_bwd<N1, N2, PURE, AK, P2>(lc.act, ch, zz, hv, zv);
 #pragma unroll
-      for (int c = 0; c < C; ++c) hb[c][i] = zv[c];
-      zb0[i] = zv[0];
+      for (int c = 0; c < C; ++c) { hb[c][i] = zv[c].v.x; hb[c][i + 1] = zv[c].v.y; }
+      zb0[i] = zv[0].v.x; zb0[i + 1] = zv[0].v.y;
     }
     const float bs = warp_reduceg(zb0, lc.lane);
     if (rlead) atomicAdd(lc.gb + ocol + re, bs);
@@ -485,11 +544,12 @@ __device__ __forceinline__ void l0_bwd_loop(const LoopCtx lc, const PassInfo<N1,
     float zv0[GW], zvd[N1 > 0 ? N1 : 1][GW];
 #pragma unroll
     for (int i = 0; i < GW; ++i) {
+      // scalar here: the packed form raises the register pressure of this loop past the 128-register budget
       float zz[C], hv[C], zv[C];
       first_layer_elem<N1, N2>(lc.fp, pi, x, g * GW + i, zz);
 #pragma unroll
       for (int c = 0; c < C; ++c) hv[c] = hb[c][i];
-      chain_bwd<N1, N2, PURE, AK>(lc.act, pi.ch, zz, hv, zv);
+      chain_bwd<N1, N2, PURE, AK, float>(lc.act, pi.ch, zz, hv, zv);
       zv0[i] = zv[0];
 #pragma unroll
       for (int jd = 0; jd < N1; ++jd) zvd[jd][i] = zv[1 + jd];
@@ -897,6 +957,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
   float* partial = args.partial + (long long)blockIdx.x * P.n_theta;
   const bool want_grad = (args.mode == 0);
   const float* theta = args.theta;
+  long long span_c0 = 0;
+  unsigned long long span_g0 = 0;
+  if (args.dbg && tid == 0) {
+    span_c0 = clock64();
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(span_g0));
+  }
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------------------------
   if (tid == 0) {
@@ -1085,6 +1151,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
   __syncthreads();
   dbg_mark(&cs, 7);
   if (tid == 0 && cs.dbg) cs.dbg[999] = cs.dbg_n;
+  if (args.dbg && tid == 0 && blockIdx.x < 250) {
+    unsigned long long g1;
+    unsigned int smid;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g1));
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    long long* rec = args.dbg + 1000 + 4 * blockIdx.x;
+    rec[0] = (long long)span_g0; rec[1] = (long long)g1; rec[2] = clock64() - span_c0; rec[3] = smid;
+  }
   if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = ms.tsum[tid];
   if (warp == 0) tc::tmem_dealloc<512>(cs.tmem);
 }

@@ -16,7 +16,7 @@ for _ in range(3):
     eng.loss_grad_host(th, None, True)
 assert lib.pinn_debug_tc_timeline(eng._h, None) == 0
 eng.loss_grad_host(th, None, True)
-buf = np.zeros(1000, dtype=np.int64)
+buf = np.zeros(2000, dtype=np.int64)
 assert lib.pinn_debug_tc_timeline(eng._h, buf.ctypes.data) == 0
 n = int(buf[999])
 ids = (buf[:n] >> 48).astype(int); clk = buf[:n] & ((1 << 48) - 1)
@@ -35,3 +35,14 @@ for i, c in zip(ids, clk):
 print("\n--- time attributed to the interval ENDING at each mark (cycles) ---")
 for k, v in sorted(agg.items(), key=lambda x: -x[1]):
     print("%8d  %5.1f%%  %s" % (v, 100.0 * v / (clk[-1] - t0), k))
+
+# per-CTA spans
+rec = buf[1000:].reshape(-1, 4)
+rec = rec[rec[:, 1] > 0]
+g0 = rec[:, 0].min()
+print("\n--- per-CTA spans: %d CTAs; start skew (ns) min %d max %d; end (ns) min %d max %d; cycles min %d median %d max %d"
+      % (len(rec), (rec[:, 0] - g0).min(), (rec[:, 0] - g0).max(), (rec[:, 1] - g0).min(), (rec[:, 1] - g0).max(),
+         rec[:, 2].min(), int(np.median(rec[:, 2])), rec[:, 2].max()))
+order = np.argsort(rec[:, 2])
+print("slowest CTAs (bid, smid, cycles, start ns, end ns):", [(int(i), int(rec[i, 3]), int(rec[i, 2]), int(rec[i, 0] - g0), int(rec[i, 1] - g0)) for i in order[-6:]])
+print("fastest CTAs:", [(int(i), int(rec[i, 3]), int(rec[i, 2])) for i in order[:6]])
