@@ -93,11 +93,14 @@ __global__ void reduce_adam_kernel(const real* __restrict__ partial, const doubl
   }
 }
 
-// after the allreduce of packed = [grad | term losses]: total = sum_k w_k L_k
+// after the allreduce of packed = [grad | term losses]: copy the gradient out and form total = sum_k w_k L_k
 template <typename real>
-__global__ void finish_kernel(const real* __restrict__ packed_terms, int n_terms, const ScaleW sw,
+__global__ void finish_kernel(const real* __restrict__ packed, long long n_grad, int n_terms, const ScaleW sw, real* out_grad,
                               real* out_terms, real* out_total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (out_grad && i < n_grad) out_grad[i] = packed[i];
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const real* packed_terms = packed + n_grad;
     double tot = 0.0;
     for (int k = 0; k < n_terms; ++k) {
       double Lk = (double)packed_terms[k];
@@ -161,14 +164,16 @@ cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* ter
   return cudaGetLastError();
 }
 
-cudaError_t finish_launch(int dtype, const void* packed_terms, int n_terms, const ScaleW& scale_w, void* out_terms,
-                          void* out_total, cudaStream_t st) {
+cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n_terms, const ScaleW& scale_w, void* out_grad,
+                          void* out_terms, void* out_total, cudaStream_t st) {
+  int blocks = (int)((n_grad + 255) / 256);
+  if (blocks < 1) blocks = 1;
   if (dtype == PINN_F64)
-    finish_kernel<double><<<1, 32, 0, st>>>((const double*)packed_terms, n_terms, scale_w, (double*)out_terms,
-                                             (double*)out_total);
+    finish_kernel<double><<<blocks, 256, 0, st>>>((const double*)packed, n_grad, n_terms, scale_w, (double*)out_grad,
+                                                   (double*)out_terms, (double*)out_total);
   else
-    finish_kernel<float><<<1, 32, 0, st>>>((const float*)packed_terms, n_terms, scale_w, (float*)out_terms,
-                                            (float*)out_total);
+    finish_kernel<float><<<blocks, 256, 0, st>>>((const float*)packed, n_grad, n_terms, scale_w, (float*)out_grad,
+                                                  (float*)out_terms, (float*)out_total);
   return cudaGetLastError();
 }
 

@@ -21,8 +21,8 @@ cudaError_t ffma_launch(int dtype, bool bufs_smem, const FfmaArgs& a, int grid, 
 cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
                           int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
                           int want_grad, cudaStream_t st);
-cudaError_t finish_launch(int dtype, const void* packed_terms, int n_terms, const ScaleW& scale_w, void* out_terms,
-                          void* out_total, cudaStream_t st);
+cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n_terms, const ScaleW& scale_w, void* out_grad,
+                          void* out_terms, void* out_total, cudaStream_t st);
 cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
                                int n_terms, const ScaleW& sw, void* theta, void* m, void* v, double lr_t, double beta1,
                                double beta2, double eps_t, void* out_terms, void* out_total, cudaStream_t st);
@@ -694,19 +694,18 @@ int pinn_loss_grad(pinn_handle e, const void* dev_theta, const double* host_weig
   if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
   e->launches += 1;
   if (e->nranks > 1) {
+    // packed = [grad (n_theta, zero-length when no gradient is wanted) | term losses]: one allreduce
+    const long long ng = dev_grad ? e->n_theta : 0;
     char* pk = (char*)e->packed;
-    void* pk_terms = pk + (size_t)e->n_theta * e->es;
-    CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw,
-                           e->packed, pk_terms, nullptr, dev_grad ? 1 : 0, st));
+    void* pk_terms = pk + (size_t)ng * e->es;
+    CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, e->packed, pk_terms, nullptr,
+                           dev_grad ? 1 : 0, st));
     e->launches += 1;
-    size_t count = (size_t)e->n_terms + (dev_grad ? (size_t)e->n_theta : 0);
-    void* base = dev_grad ? e->packed : pk_terms;
-    ncclResult_t r = g_nccl.AllReduce(base, base, count, e->dtype == PINN_F64 ? ncclFloat64 : ncclFloat32, ncclSumOp,
-                                      e->comm, st);
+    ncclResult_t r = g_nccl.AllReduce(e->packed, e->packed, (size_t)ng + (size_t)e->n_terms,
+                                      e->dtype == PINN_F64 ? ncclFloat64 : ncclFloat32, ncclSumOp, e->comm, st);
     if (r != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
     e->launches += 1;
-    if (dev_grad) CUDA_TRY(cudaMemcpyAsync(dev_grad, e->packed, (size_t)e->n_theta * e->es, cudaMemcpyDeviceToDevice, st));
-    CUDA_TRY(finish_launch(e->dtype, pk_terms, e->n_terms, sw, dev_term_losses, dev_total, st));
+    CUDA_TRY(finish_launch(e->dtype, e->packed, ng, e->n_terms, sw, dev_grad, dev_term_losses, dev_total, st));
     e->launches += 1;
   } else {
     CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, dev_grad,

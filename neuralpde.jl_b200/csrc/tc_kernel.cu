@@ -340,9 +340,16 @@ template <int N1, int N2>
 __device__ __forceinline__ void first_layer_elem(uint32_t fpa, const PassInfo<N1, N2>& pi, const float (&x)[PINN_MAX_IN],
                                                  int o, float* zz) {
   float s = lds_f32(fpa + (FP_B1 + o) * 4);
+  const uint32_t wa = fpa + (FP_W1 + o * 8) * 4;
+  if (pi.d_in <= 3) {            // common 1-D / 2-D / 3-D problems: no predicated tail
+    s = fmaf(lds_f32(wa), x[0], s);
+    if (pi.d_in >= 2) s = fmaf(lds_f32(wa + 4), x[1], s);
+    if (pi.d_in == 3) s = fmaf(lds_f32(wa + 8), x[2], s);
+  } else {
 #pragma unroll
-  for (int k = 0; k < PINN_MAX_IN; ++k)
-    if (k < pi.d_in) s = fmaf(lds_f32(fpa + (FP_W1 + o * 8 + k) * 4), x[k], s);
+    for (int k = 0; k < PINN_MAX_IN; ++k)
+      if (k < pi.d_in) s = fmaf(lds_f32(wa + k * 4), x[k], s);
+  }
   zz[0] = s;
 #pragma unroll
   for (int j = 0; j < N1; ++j) zz[1 + j] = lds_f32(fpa + (FP_W1 + o * 8 + pi.dir1[j]) * 4);
@@ -511,6 +518,38 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
     if (rlead) atomicAdd(lc.gb + ocol + re, bs);
 #pragma unroll
     for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tP, lc.p, ocol, hb[c], false);
+  }
+}
+
+// layer 0 backward, tensor-core variant: adjoints of H^0 (TMEM X) -> Zbar^0 tiles (value + first-derivative
+// channels; bf16 hi) in P.  The weight / bias gradient is then one small MMA chain against the augmented
+// coordinate tiles (see net_backward), so no cross-lane reductions are needed here.
+template <int N1, int N2, bool PURE, int AK>
+__device__ __forceinline__ void l0_bwd_store_loop(const LoopCtx lc, const PassInfo<N1, N2> pi, const float* xp) {
+  constexpr int C = 1 + N1 + N2;
+  float x[PINN_MAX_IN];
+#pragma unroll
+  for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = xp[k];
+#pragma unroll 1
+  for (int g = lc.g0; g < lc.g1; ++g) {
+    float hb[C][GWB];
+#pragma unroll
+    for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + g * GWB, hb[c]);
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < GWB; i += 2) {
+      float za[C], zb2[C];
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GWB + i, za);
+      first_layer_elem<N1, N2>(lc.fp, pi, x, g * GWB + i + 1, zb2);
+      P2 zz[C], hv[C], zv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { zz[c] = mk2(za[c], zb2[c]); hv[c] = mk2(hb[c][i], hb[c][i + 1]); }
+      chain_bwd<N1, N2, PURE, AK, P2>(lc.act, pi.ch, zz, hv, zv);
+#pragma unroll
+      for (int c = 0; c <= N1; ++c) { hb[c][i] = zv[c].v.x; hb[c][i + 1] = zv[c].v.y; }
+    }
+#pragma unroll
+    for (int c = 0; c <= N1; ++c) store_half(lc.tP + c * kTileBytes, lc.tP, lc.p, g * GWB, hb[c], false);
   }
 }
 
@@ -896,7 +935,7 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
     }
   }
 
-  // ---- layer 0 backward on the CUDA cores ---------------------------------------------------------------------------------------
+  // ---- layer 0 backward ---------------------------------------------------------------------------------------------------
   {
     tc::tc_fence_before();
     __syncthreads();
@@ -905,13 +944,84 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
     const int act0 = net.acts[0];
     float* gb0 = partial + net.b_off[0];
     float* gw0 = partial + net.w_off[0];
-    const int ng = pi.n1w / GW;
     LoopCtx lc;
     lc.fp = tc::smem_u32(fp); lc.bt = lc.fp; lc.tP = tc::smem_u32(tP); lc.tQ = tc::smem_u32(tQ); lc.gb = gb0; lc.gw = gw0;
-    lc.taddr = tmem + t.lane_addr;
-    lc.act = act0; lc.split = 0; lc.p = p; lc.lane = lane; lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
-    lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
-    l0_bwd_loop<N1, N2, PURE, AK>(lc, pi, x, ub);
+    lc.taddr = tmem + t.lane_addr; lc.act = act0; lc.split = 0; lc.p = p; lc.lane = lane; lc.c0 = 0; lc.flag = (TL == 0) ? 1 : 0;
+    if (TL == 0) {
+      // no tensor layer: everything on the CUDA cores (warp reduce-scatter + atomics)
+      const int ng = pi.n1w / GW;
+      lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
+      l0_bwd_loop<N1, N2, PURE, AK>(lc, pi, x, ub);
+    } else {
+      // Wbar_0[o][k] = sum_p zbar_0[p][o] x_k[p] + zbar_(1+j)[p][o] [dir1[j] == k],  bbar_0[o] = sum_p zbar_0[p][o]:
+      // one MMA chain  D[o][0..15] = Zbar_0^T [x | 1] + sum_j Zbar_(1+j)^T E_(dir1[j])  with K = the 128 points.
+      // B tiles (rows = points, 16 columns used) live in Q, which is free after the last tensor layer:
+      //   tile 0: bf16 hi of (x_0..x_7) in columns 0..7, 1.0 in column 8;  tile 1+j: 1.0 in column dir1[j];
+      //   tile 1+N1: bf16 lo of x (only when the channel count leaves a spare tile, i.e. N2 > 0)
+      if (tid < kTcPts) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          hi[k] = tc::pack_bf16(x[2 * k], x[2 * k + 1]);
+          lo[k] = tc::pack_bf16(x[2 * k] - __uint_as_float(hi[k] << 16), x[2 * k + 1] - __uint_as_float(hi[k] & 0xffff0000u));
+        }
+        const uint32_t q0 = tc::smem_u32(tQ);
+        const uint32_t c0a = tc::swz_chunk(p, 0), c1a = tc::swz_chunk(p, 1);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + c0a), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + c1a), "r"(0x00003f80u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        if (N2 > 0) {
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + (1 + N1) * kTileBytes + c0a), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + (1 + N1) * kTileBytes + c1a), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        }
+#pragma unroll
+        for (int j = 0; j < N1; ++j) {
+          const int d = pi.dir1[j];
+          uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) w[k] = (d == 2 * k) ? 0x00003f80u : ((d == 2 * k + 1) ? 0x3f800000u : 0u);
+          const uint32_t qb = q0 + (1 + j) * kTileBytes;
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(qb + c0a), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(qb + c1a), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+        }
+      }
+      const int ng = pi.n1w / GWB;
+      lc.g0 = hh * (ng / kNH); lc.g1 = (hh + 1) * (ng / kNH);
+      l0_bwd_store_loop<N1, N2, PURE, AK>(lc, pi, x);
+      tc::fence_async_smem();
+      tc::tc_fence_before();
+      __syncthreads();
+      if (tc::uni(t.warp) == 0) {
+        const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_Q = tc::uni(tc::smem_u32(tQ));
+        if (tc::elect_one()) {
+          tc::tc_fence_after();
+          const uint32_t idesc = tc::make_idesc(128, 16, 1, 1);
+          const uint64_t a0 = tc::make_desc(u_P, 0, 1024);
+          mma_chain(u_tmem + TM_Y, a0, tc::make_desc(u_Q, 0, 1024), 2048, 2048, kTcPts / 16, idesc, 0);
+          if (N2 > 0)
+            mma_chain(u_tmem + TM_Y, a0, tc::make_desc(u_Q + (1 + N1) * kTileBytes, 0, 1024), 2048, 2048, kTcPts / 16, idesc, 1);
+#pragma unroll 1
+          for (int j = 0; j < N1; ++j)
+            mma_chain(u_tmem + TM_Y, tc::make_desc(u_P + (1 + j) * kTileBytes, 0, 1024),
+                      tc::make_desc(u_Q + (1 + j) * kTileBytes, 0, 1024), 2048, 2048, kTcPts / 16, idesc, 1);
+          tc::mma_commit(ms.bar_mma);
+        }
+        __syncwarp();
+      }
+      wait_bar(ms.bar_mma, mma_phase);
+      tc::tc_fence_after();
+      if (q < 2 && hh == 0) {
+        const int o = q * 32 + lane;
+        float v[16];
+        tc::tmem_ld16(tmem + t.lane_addr + TM_Y, v);
+        tc::tmem_ld_wait();
+        if (o < pi.n1w) {
+#pragma unroll
+          for (int k = 0; k < PINN_MAX_IN; ++k)
+            if (k < pi.d_in) atomicAdd(gw0 + o + (long long)pi.n1w * k, v[k]);
+          atomicAdd(gb0 + o, v[8]);
+        }
+      }
+    }
   }
   __syncthreads();
   dbg_mark(cs, 30);
@@ -1006,33 +1116,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
       fp[FP_W1 + o * 8 + k] = __ldg(&theta[w0 + i]);
     }
     for (int i = tid; i < n1w; i += kTcThreads) fp[FP_B1 + i] = __ldg(&theta[b0 + i]);
-    for (int l = 1; l <= L - 2; ++l) {
+    // thread <-> (layer, row o, chunk of 8 k): one flattened loop keeps all layers' loads in flight
+    for (int i = tid; i < (L - 2) * 64 * 8; i += kTcThreads) {
+      const int l = 1 + i / 512, r = i & 511;
+      const int o = r & 63, kc = r >> 6;
       const int n_in = net.dims[l], n_out = net.dims[l + 1];
-      const long long woff = net.w_off[l], boff = net.b_off[l];
+      const long long woff = net.w_off[l];
       uint8_t* thi = smem + ns.w_hi[l - 1];
       uint8_t* tlo = smem + ns.w_lo[l - 1];
-      // thread <-> (row o, chunk of 8 k): coalesced-ish reads along o, one 16-byte swizzled store
-      for (int i = tid; i < 64 * 8; i += kTcThreads) {
-        const int o = i & 63, kc = i >> 6;
-        float w[8];
+      float w[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int k = kc * 8 + e;
-          w[e] = (o < n_out && k < n_in) ? __ldg(&theta[woff + o + (long long)n_out * k]) : 0.f;
-        }
-        uint4 h, lo4;
-        h.x = tc::pack_bf16(w[0], w[1]); h.y = tc::pack_bf16(w[2], w[3]);
-        h.z = tc::pack_bf16(w[4], w[5]); h.w = tc::pack_bf16(w[6], w[7]);
-        *reinterpret_cast<uint4*>(thi + tc::swz_chunk(o, kc)) = h;
-        if (args.split) {
-          lo4.x = tc::pack_bf16(w[0] - __uint_as_float(h.x << 16), w[1] - __uint_as_float(h.x & 0xffff0000u));
-          lo4.y = tc::pack_bf16(w[2] - __uint_as_float(h.y << 16), w[3] - __uint_as_float(h.y & 0xffff0000u));
-          lo4.z = tc::pack_bf16(w[4] - __uint_as_float(h.z << 16), w[5] - __uint_as_float(h.z & 0xffff0000u));
-          lo4.w = tc::pack_bf16(w[6] - __uint_as_float(h.w << 16), w[7] - __uint_as_float(h.w & 0xffff0000u));
-          *reinterpret_cast<uint4*>(tlo + tc::swz_chunk(o, kc)) = lo4;
-        }
+      for (int e = 0; e < 8; ++e) {
+        const int k = kc * 8 + e;
+        w[e] = (o < n_out && k < n_in) ? __ldg(&theta[woff + o + (long long)n_out * k]) : 0.f;
       }
-      for (int i = tid; i < n_out; i += kTcThreads) fp[FP_BT + (l - 1) * 64 + i] = __ldg(&theta[boff + i]);
+      uint4 h, lo4;
+      h.x = tc::pack_bf16(w[0], w[1]); h.y = tc::pack_bf16(w[2], w[3]);
+      h.z = tc::pack_bf16(w[4], w[5]); h.w = tc::pack_bf16(w[6], w[7]);
+      *reinterpret_cast<uint4*>(thi + tc::swz_chunk(o, kc)) = h;
+      if (args.split) {
+        lo4.x = tc::pack_bf16(w[0] - __uint_as_float(h.x << 16), w[1] - __uint_as_float(h.x & 0xffff0000u));
+        lo4.y = tc::pack_bf16(w[2] - __uint_as_float(h.y << 16), w[3] - __uint_as_float(h.y & 0xffff0000u));
+        lo4.z = tc::pack_bf16(w[4] - __uint_as_float(h.z << 16), w[5] - __uint_as_float(h.z & 0xffff0000u));
+        lo4.w = tc::pack_bf16(w[6] - __uint_as_float(h.w << 16), w[7] - __uint_as_float(h.w & 0xffff0000u));
+        *reinterpret_cast<uint4*>(tlo + tc::swz_chunk(o, kc)) = lo4;
+      }
+    }
+    for (int i = tid; i < (L - 2) * 64; i += kTcThreads) {
+      const int l = 1 + i / 64, o = i & 63;
+      if (o < net.dims[l + 1]) fp[FP_BT + (l - 1) * 64 + o] = __ldg(&theta[net.b_off[l] + o]);
     }
     const int nL = net.dims[L - 1];
     const long long wl = net.w_off[L - 1], bl = net.b_off[L - 1];
