@@ -104,6 +104,14 @@ struct pinn_engine {
   TcNetSmem tc_nets[PINN_MAX_NETS];
   long long tc_stash_per_cta = 0;
   long long* tc_dbg = nullptr;   // device buffer for pinn_debug_tc_timeline
+  // wide tensor path (128-wide layers): streamed weights, fp32 pre-activation stash
+  bool tw = false;
+  int tw_off_P = 0, tw_off_S = 0, tw_off_misc = 0, tw_off_fp[PINN_MAX_NETS], tw_wimg[PINN_MAX_NETS];
+  int tw_n_images = 0;
+  unsigned char tw_img_net[kTwMaxImages], tw_img_layer[kTwMaxImages];
+  long long tw_hstash_per_cta = 0, tw_zstash_per_cta = 0;
+  void* tw_wpack = nullptr;
+  void* tw_zstash = nullptr;
   // workspaces (device)
   void* partial = nullptr;
   double* term_sums = nullptr;
@@ -417,6 +425,7 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
   e->tc_split = d->mode == PINN_MODE_TC_SPLIT ? 1 : 0;
   e->tile_pts = kTcPts;
   int tl_max = 0;
+  bool wide = false;
   for (int k = 0; k < d->n_nets; ++k) {
     const DevNet& n = P.nets[k];
     if (n.n_layers < 2) return fail("pinn_create(tc): net %d needs at least 2 Dense layers", k);
@@ -424,13 +433,29 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
     if (n.acts[n.n_layers - 1] != PINN_ACT_IDENTITY)
       return fail("pinn_create(tc): net %d: the last layer must be linear (identity activation)", k);
     for (int l = 1; l < n.n_layers; ++l)
-      if (n.dims[l] % 16 != 0 || n.dims[l] < 16 || n.dims[l] > 64)
-        return fail("pinn_create(tc): net %d hidden width %d unsupported by the tcgen05 path (16, 32, 48 or 64; use "
-                    "PINN_MODE_FFMA for other shapes)", k, n.dims[l]);
+      if (n.dims[l] > 64) wide = true;
     if (n.n_layers - 2 > kTcMaxTL)
       return fail("pinn_create(tc): net %d has %d hidden->hidden layers (max %d)", k, n.n_layers - 2, kTcMaxTL);
     tl_max = std::max(tl_max, n.n_layers - 2);
   }
+  for (int k = 0; k < d->n_nets; ++k) {
+    const DevNet& n = P.nets[k];
+    for (int l = 1; l < n.n_layers; ++l) {
+      const int w = n.dims[l];
+      if (!wide && (w % 16 != 0 || w < 16 || w > 64))
+        return fail("pinn_create(tc): net %d hidden width %d unsupported by the tcgen05 path (16, 32, 48, 64, or 64/128 "
+                    "with PINN_MODE_TC_BF16; use PINN_MODE_FFMA for other shapes)", k, w);
+      if (wide && w != 64 && w != 128)
+        return fail("pinn_create(tc): net %d hidden width %d: networks with layers wider than 64 need every hidden width "
+                    "to be 64 or 128 on the tcgen05 path (use PINN_MODE_FFMA for other shapes)", k, w);
+    }
+    if (wide && n.n_layers < 3)
+      return fail("pinn_create(tc): net %d: the 128-wide tcgen05 path needs at least one hidden->hidden layer", k);
+  }
+  if (wide && d->mode != PINN_MODE_TC_BF16)
+    return fail("pinn_create(tc): PINN_MODE_TC_SPLIT supports hidden widths up to 64; 128-wide layers run in "
+                "PINN_MODE_TC_BF16 (or PINN_MODE_FFMA for fp32 accuracy)");
+  e->tw = wide;
   int n_used_max = 1;
   for (int t = 0; t < d->n_terms; ++t) {
     const DevTerm& T = P.terms[t];
@@ -442,6 +467,9 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       const int ok[] = {0, 8, 16, 24, 32, 9, 17, 25, 18};
       bool found = false;
       for (int v : ok) found = found || v == key;
+      if (wide && (ch.C > kTwMaxC || key == 32))
+        return fail("pinn_create(tc): term %d needs %d channels on a 128-wide network; the tcgen05 path propagates at most "
+                    "%d there (use PINN_MODE_FFMA)", t, ch.C, kTwMaxC);
       if (!found || ch.C > kTcMaxC)
         return fail("pinn_create(tc): term %d needs %d first + %d second derivative channels; the tcgen05 path "
                     "propagates at most %d channels per network (use PINN_MODE_FFMA)", t, ch.n1, ch.n2, kTcMaxC);
@@ -450,6 +478,39 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       if (T.tap_out[i] != 0) return fail("pinn_create(tc): term %d tap %d: output component must be 0", t, i);
   }
   e->tc_tl_max = tl_max;
+  if (wide) {
+    for (int t = 0; t < d->n_terms; ++t)
+      if (P.terms[t].n_used > 1)
+        return fail("pinn_create(tc): term %d couples %d networks; the 128-wide tcgen05 path handles one network per "
+                    "term (use PINN_MODE_FFMA)", t, P.terms[t].n_used);
+    int maxCw = 1;
+    for (int t = 0; t < d->n_terms; ++t) maxCw = std::max(maxCw, (int)P.terms[t].chan[0].C);
+    size_t o2 = 0;
+    e->tw_off_P = (int)o2; o2 += (size_t)maxCw * kTwNB * kTileBytes;
+    e->tw_off_S = (int)o2; o2 += (size_t)2 * kTwImgBytes;
+    e->tw_n_images = 0;
+    for (int k = 0; k < PINN_MAX_NETS; ++k) { e->tw_off_fp[k] = -1; e->tw_wimg[k] = 0; }
+    for (int k = 0; k < d->n_nets; ++k) {
+      e->tw_off_fp[k] = (int)o2;
+      o2 += ((size_t)FW_SIZE * 4 + 15) & ~size_t(15);
+      e->tw_wimg[k] = e->tw_n_images;
+      for (int l = 1; l <= P.nets[k].n_layers - 2; ++l) {
+        e->tw_img_net[e->tw_n_images] = (unsigned char)k;
+        e->tw_img_layer[e->tw_n_images] = (unsigned char)l;
+        ++e->tw_n_images;
+      }
+    }
+    e->tw_off_misc = (int)o2;
+    o2 += tc_misc_bytes();
+    if (o2 + 1024 > (size_t)max_smem)
+      return fail("pinn_create(tc): the problem needs %zu bytes of shared memory per CTA (limit %d): too many networks "
+                  "for the 128-wide tcgen05 path", o2, max_smem);
+    e->smem = o2;
+    e->tw_hstash_per_cta = (long long)tl_max * kTwMaxC * kTwNB * kTileBytes;
+    e->tw_zstash_per_cta = (long long)tl_max * kTwMaxC * 64 * kTcPts * 2;      // floats
+    e->tc_stash_per_cta = e->tw_hstash_per_cta;
+    return 0;
+  }
   size_t off = 0;
   e->tc_off_P = (int)off; off += (size_t)maxC * kTileBytes;
   e->tc_off_Q = (int)off; off += (size_t)maxC * kTileBytes;
@@ -489,7 +550,7 @@ int pinn_destroy(pinn_handle e) {
   cudaSetDevice(e->device);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   void* ptrs[] = {e->dprob, e->partial, e->term_sums, e->stash, e->gbufs, e->packed,
-                  e->d_theta, e->d_grad, e->d_out, e->adam_m, e->adam_v};
+                  e->d_theta, e->d_grad, e->d_out, e->adam_m, e->adam_v, e->tw_wpack, e->tw_zstash};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int t = 0; t < PINN_MAX_TERMS; ++t) {
     if (e->own_pts[t]) cudaFree(e->own_pts[t]);
@@ -541,6 +602,10 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
     if (!e->bufs_smem) TRY_OR_DESTROY(dev_alloc(&e->gbufs, g * 2 * (size_t)e->buf_elems * e->es, e));
   } else {
     TRY_OR_DESTROY(dev_alloc(&e->stash, g * (size_t)e->tc_stash_per_cta, e));
+    if (e->tw) {
+      TRY_OR_DESTROY(dev_alloc(&e->tw_zstash, g * (size_t)e->tw_zstash_per_cta * sizeof(float), e));
+      TRY_OR_DESTROY(dev_alloc(&e->tw_wpack, (size_t)std::max(e->tw_n_images, 1) * kTwImgBytes, e));
+    }
   }
   TRY_OR_DESTROY(dev_alloc(&e->packed, ((size_t)e->n_theta + PINN_MAX_TERMS) * e->es, e));
   TRY_OR_DESTROY(dev_alloc(&e->d_theta, (size_t)e->n_theta * e->es, e));
@@ -648,6 +713,36 @@ static void fill_args(pinn_engine* e, FfmaArgs& a, const void* theta, int mode) 
 static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_t st) {
   if (e->mode == PINN_MODE_FFMA) {
     CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, st));
+    return 0;
+  }
+  if (e->tw) {
+    TwPackArgs pk;
+    memset(&pk, 0, sizeof pk);
+    pk.prob = a.prob; pk.theta = (const float*)a.theta; pk.wpack = (uint8_t*)e->tw_wpack; pk.n_images = e->tw_n_images;
+    memcpy(pk.img_net, e->tw_img_net, sizeof pk.img_net);
+    memcpy(pk.img_layer, e->tw_img_layer, sizeof pk.img_layer);
+    CUDA_TRY(tw_pack_launch(pk, st));
+    e->launches += 1;
+    TwArgs w;
+    memset(&w, 0, sizeof w);
+    w.prob = a.prob; w.theta = (const float*)a.theta; w.partial = (float*)a.partial; w.term_sums = a.term_sums;
+    w.hstash = (uint8_t*)e->stash; w.hstash_per_cta = e->tw_hstash_per_cta;
+    w.zstash = (float*)e->tw_zstash; w.zstash_per_cta = e->tw_zstash_per_cta;
+    w.wpack = (const uint8_t*)e->tw_wpack; w.tl_max = std::max(e->tc_tl_max, 1);
+    w.tile_begin = a.tile_begin; w.tile_end = a.tile_end; w.mode = a.mode; w.resid_out = (float*)a.resid_out;
+    w.dbg = e->tc_dbg;
+    w.off_P = e->tw_off_P; w.off_S = e->tw_off_S; w.off_misc = e->tw_off_misc;
+    for (int k = 0; k < PINN_MAX_NETS; ++k) {
+      w.off_fp[k] = e->tw_off_fp[k]; w.wimg[k] = e->tw_wimg[k];
+      int ak = 1;
+      if (k < e->hprob->n_nets) {
+        const DevNet& n = e->hprob->nets[k];
+        for (int l = 0; l + 1 < n.n_layers; ++l) if (n.acts[l] != PINN_ACT_TANH) ak = 0;
+      }
+      w.net_ak[k] = ak;
+    }
+    for (int k = 0; k < PINN_MAX_TERMS; ++k) { w.seed[k] = a.seed[k]; w.dyn[k] = a.dyn[k]; }
+    CUDA_TRY(tw_launch(w, grid, e->smem, st));
     return 0;
   }
   TcArgs t;

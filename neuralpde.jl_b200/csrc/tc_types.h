@@ -53,6 +53,55 @@ struct TcArgs {
   TermDyn dyn[PINN_MAX_TERMS];
 };
 
+
+// ---- wide path (tc_wide_kernel.cu): hidden widths 64 / 128, bf16 operands, weights streamed per layer ---------------
+constexpr int kTwMaxC = 4;             // channels per network: C x 128 TMEM columns
+constexpr int kTwW = 128;              // TMEM column stride of a channel = widest supported layer
+constexpr int kTwNB = 2;               // 64-column operand tiles per channel
+constexpr int kTwImgBytes = kTwNB * kTileBytes;   // packed bf16 image of one tensor layer's weight: [kb][128 rows o][64 k]
+// fp32 parameter block per network (floats)
+constexpr int FW_W1 = 0;               // [128][8] first-layer weight
+constexpr int FW_B1 = 1024;            // [128]
+constexpr int FW_BT = 1152;            // [kTcMaxTL][128] tensor-layer biases
+constexpr int FW_WL = FW_BT + kTcMaxTL * 128;   // [128] last-layer weight
+constexpr int FW_BL = FW_WL + 128;     // [1]
+constexpr int FW_SIZE = FW_BL + 4;
+constexpr int kTwMaxImages = PINN_MAX_NETS * kTcMaxTL;
+
+struct TwArgs {
+  const DevProblem* prob;
+  const float* theta;
+  float* partial;          // [grid][n_theta]
+  double* term_sums;       // [grid][PINN_MAX_TERMS]
+  uint8_t* hstash;         // [grid][hstash_per_cta] bf16 operand tiles: input of tensor layer l, [slot][l-1][c][kb]
+  long long hstash_per_cta;
+  float* zstash;           // [grid][zstash_per_cta floats] fp32 pre-activations, [slot][l-1][c][col/2][point] float2
+  long long zstash_per_cta;
+  const uint8_t* wpack;    // packed weight images, kTwImgBytes each
+  int wimg[PINN_MAX_NETS]; // image index of a network's first tensor layer
+  int tl_max;
+  int tile_begin, tile_end;
+  int mode;                // 0 loss+grad, 1 loss only, 2 residual out
+  float* resid_out;
+  long long* dbg;
+  int off_P, off_S, off_misc;       // byte offsets into dynamic shared memory (P: C x 2 tiles, S: 2 x 32 KB)
+  int off_fp[PINN_MAX_NETS];        // fp32 parameter block per network (-1: unused)
+  int net_ak[PINN_MAX_NETS];
+  double seed[PINN_MAX_TERMS];
+  TermDyn dyn[PINN_MAX_TERMS];
+};
+
+struct TwPackArgs {
+  const DevProblem* prob;
+  const float* theta;
+  uint8_t* wpack;
+  int n_images;
+  unsigned char img_net[kTwMaxImages], img_layer[kTwMaxImages];
+};
+
+cudaError_t tw_pack_launch(const TwPackArgs& a, cudaStream_t st);
+cudaError_t tw_launch(const TwArgs& a, int grid, size_t smem, cudaStream_t st);
+
 size_t tc_misc_bytes();
 cudaError_t tc_launch(const TcArgs& a, int grid, size_t smem, cudaStream_t st);
 

@@ -36,12 +36,27 @@ def neumann_sin_case() -> Config:
     return Config("neumann_sin", sys_, [chain], GridTraining(1.0 / 63), n_pde_points=64)
 
 
+def poisson1d_wide_case() -> Config:
+    """1-D Poisson with a Neumann end on a 1 -> 128 -> 64 -> 128 -> 1 network: the 128-wide tensor path with mixed
+    64 / 128 layer widths and 3 / 2 / 1 propagated channels (PDE, Neumann, Dirichlet terms)."""
+    x = parameters("x")
+    u = variables("u")
+    Dx = Differential(x)
+    eq = Eq((Dx ** 2)(u(x)), -sp.pi ** 2 * sp.sin(sp.pi * x))
+    bcs = [Eq(u(0.0), 0.0), Eq(Dx(u(1.0)), -sp.pi)]
+    sys_ = PDESystem(eq, bcs, [In(x, 0.0, 1.0)], [x], [u(x)])
+    chain = Chain(Dense(1, 128, "tanh"), Dense(128, 64, "tanh"), Dense(64, 128, "tanh"), Dense(128, 1))
+    return Config("poisson1d_wide", sys_, [chain], GridTraining(1.0 / 299), n_pde_points=300)
+
+
 CASES = {
     "cfg1": lambda: configs.config1(),
     "cfg2_small": lambda: configs.config2(n=24, width=16, hidden=2),
     "cfg3_small": lambda: configs.config3(points=512, bcs_points=96, width=32, hidden=3),
     "cfg4_tiny": lambda: configs.config4(nodes=4, bc_nodes=3, width=16, hidden=2),
     "cfg5_small": lambda: configs.config5(points=384, bcs_points=64, n_obs=80, width=16, hidden=2),
+    "burgers_wide": lambda: configs.config3(points=700, bcs_points=150, width=128, hidden=3),
+    "poisson1d_wide": poisson1d_wide_case,
     "mixed": mixed_derivative_case,
     "neumann_sin": neumann_sin_case,
 }

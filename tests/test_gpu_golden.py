@@ -52,6 +52,39 @@ def test_tc_bf16_loss_rtol_1e2(name):
     assert rel(grad, g["grad"]) < 2e-2
 
 
+WIDE_CASES = ["burgers_wide", "poisson1d_wide"]
+
+
+@pytest.mark.parametrize("name", WIDE_CASES)
+def test_tc_wide_bf16_loss_rtol_1e2(name):
+    """128-wide layers on the tcgen05 path (bf16 operands, streamed weights, fp32 pre-activation stash; BASELINE config 3
+    names this mode): same stated tolerance as the narrow bf16 mode, loss 1e-2 / gradient 2e-2."""
+    g, sets, qw = load_golden(name)
+    rep, total, terms, grad = engine_eval_sets(CASES[name](), np.float32, sets, qw, mode="tc_bf16", theta=g["theta"])
+    assert abs(total - float(g["total"])) <= 1e-2 * abs(float(g["total"])), (total, float(g["total"]))
+    np.testing.assert_allclose(terms, g["terms"], rtol=2e-2)
+    assert rel(grad, g["grad"]) < 2e-2
+
+
+@pytest.mark.parametrize("name", WIDE_CASES)
+def test_tc_wide_loss_only_and_residual_probe(name):
+    """loss-only evaluation (no gradient, no stash) and the per-point residual probe on the wide path"""
+    g, sets, qw = load_golden(name)
+    cfg = CASES[name]()
+    rep, total, terms, grad = engine_eval_sets(cfg, np.float32, sets, qw, mode="tc_bf16", theta=g["theta"], want_grad=False)
+    assert grad is None
+    assert abs(total - float(g["total"])) <= 1e-2 * abs(float(g["total"]))
+    r = rep.engine.term_residual_host(0, np.asarray(g["theta"], dtype=np.float32), sets[0].shape[1])
+    assert r.shape == (sets[0].shape[1],) and np.isfinite(r).all()
+    assert abs(float(np.mean(r.astype(np.float64) ** 2)) - float(g["terms"][0])) <= 2e-2 * float(g["terms"][0])
+
+
+def test_tc_split_rejects_wide_layers_loudly():
+    g, sets, qw = load_golden("burgers_wide")
+    with pytest.raises(npde.EngineError, match="widths up to 64"):
+        engine_eval_sets(CASES["burgers_wide"](), np.float32, sets, qw, mode="tc_split", theta=g["theta"])
+
+
 @pytest.mark.parametrize("name", ["mixed", "cfg4_tiny", "cfg5_small"])
 def test_tc_rejects_unsupported_shapes_loudly(name):
     """More than 5 propagated channels per network: the tcgen05 path refuses (no silent fallback)."""
