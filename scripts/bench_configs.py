@@ -9,11 +9,13 @@ from neuralpde_jl_b200 import configs
 
 cases = [("cfg1", configs.config1(), ["ffma", "tc_split"]),
          ("cfg2", configs.config2(), ["ffma", "tc_split", "tc_bf16"]),
-         ("cfg3 (65536 pts, 5x128)", configs.config3(), ["ffma"]),
+         ("cfg3 (65536 pts, 5x128)", configs.config3(), ["ffma", "tc_bf16"]),
          ("cfg5 (262144 pts = 1M/4 GPUs, 4x128)", configs.config5(points=1 << 18, bcs_points=4096), ["ffma"]),
          ("cfg4 (32^3 nodes, 4 nets 6x256)", configs.config4(nodes=32, bc_nodes=16), ["ffma"])]
 dev = torch.device("cuda")
+only = sys.argv[1:]
 for name, cfg, modes in cases:
+    if only and not any(name.startswith(o) for o in only): continue
     for mode in modes:
         try:
             rep = npde.symbolic_discretize(cfg.pde_system, cfg.discretization(dtype=np.float32, mode=mode))

@@ -5,9 +5,12 @@ sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import neuralpde_jl_b200 as npde
 from neuralpde_jl_b200 import configs
 mode = sys.argv[1] if len(sys.argv) > 1 else "tc_split"
-cfg = configs.config2()
+which = sys.argv[2] if len(sys.argv) > 2 else "cfg2"
+cfg = configs.config3() if which == "cfg3" else configs.config2()
 rep = npde.symbolic_discretize(cfg.pde_system, cfg.discretization(dtype=np.float32, mode=mode))
 eng = rep.engine
+if hasattr(rep.strategy, "points"):
+    rep.loss_functions.full_loss_function(rep.flat_init_params)     # draws the first sample
 lib = eng.lib
 lib.pinn_debug_tc_timeline.argtypes = [C.c_void_p, C.c_void_p]
 lib.pinn_debug_tc_timeline.restype = C.c_int
@@ -25,6 +28,9 @@ names = {1: "start", 2: "setup done", 3: "tile loaded", 4: "fwd done", 5: "progr
          15: "F epilogues done", 16: "F exit", 20: "B enter", 21: "B l: start", 22: "B l: stash loaded", 23: "B g: sync",
          24: "B g: refwd issued", 25: "B g: refwd done", 26: "B l: zbar written+sync", 27: "B l: dgrad+wgrad issued",
          28: "B l: dgrad+wgrad done", 29: "B l0 start", 30: "B exit"}
+if which == "cfg3":     # marks of the 128-wide kernel (tc_wide_kernel.cu)
+    names.update({21: "B l: start", 26: "B l: zbar epilogue+sync", 27: "B l: wgrad issued (issuing lane waits H tiles)",
+                  28: "B l: wgrad done", 29: "B l: dgrad done + wgrad flushed"})
 t0 = clk[0]
 prev = t0
 agg = {}
