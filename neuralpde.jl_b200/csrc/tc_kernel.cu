@@ -460,51 +460,60 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
         for (int c = 0; c < C; ++c) ub[c] += (tch == c) ? g : 0.f;
       }
   }
-  // ---- last layer: bias and weight gradient on the CUDA cores -------------------------------------------------------
+  // ---- last layer: bias gradient by warp sums; weight gradient  wbar_last[o] = sum_{c,p} ubar_c[p] H_c^{L-2}[p][o]  on the
+  // tensor core: D_c[o][0..15] = H_c^T U with U[p] = (hi, lo) bf16 pairs of ubar_0..ubar_(C-1) (columns 2c, 2c+1) ------------
   {
     float* gb_last = partial + net.b_off[L - 1];
     float* gw_last = partial + net.w_off[L - 1];
     if (hh == 0) {
       const float s = warp_sum<float>(ub[0]);
       if (lane == 0) atomicAdd(gb_last, s);
+      uint32_t w[8];
 #pragma unroll
-      for (int c = 0; c < C; ++c) ms.scratch[c * kTcPts + p] = ub[c];
+      for (int c = 0; c < 8; ++c) w[c] = 0u;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const uint32_t hi = tc::pack_bf16(ub[c], 0.f) & 0xffffu;
+        const float r = ub[c] - __uint_as_float(hi << 16);
+        w[c] = hi | (tc::pack_bf16(r, 0.f) << 16);
+      }
+      const uint32_t q0 = tc::smem_u32(tQ);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + tc::swz_chunk(p, 0)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + tc::swz_chunk(p, 1)), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
     }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
     __syncthreads();
-    // wbar_last[o] = sum_{c,p} ubar_c[p] * H_c^{L-2}[p][o]; P still holds H^{L-2} (bf16 hi).
-    // lane <-> (16-byte chunk j = lane & 7 of 8 neurons, point sub-group lane >> 3); warps stride the points
-    const int j = lane & 7;
-    {
-      const bool jvalid = j * 8 < pi.nL;       // all lanes run the loop and the shuffles; only valid chunks load / add
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int pp = t.warp * 4 + (lane >> 3); pp < kTcPts; pp += (kTcThreads / 32) * 4) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          uint4 h = make_uint4(0u, 0u, 0u, 0u);
-          if (jvalid) h = *reinterpret_cast<const uint4*>(tP + c * kTileBytes + tc::swz_chunk(pp, j));
-          const float uc = ms.scratch[c * kTcPts + pp];
-          const uint32_t w[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[2 * i] = fmaf(uc, __uint_as_float(w[i] << 16), acc[2 * i]);
-            acc[2 * i + 1] = fmaf(uc, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
-          }
-        }
+    if (tc::uni(t.warp) == 0) {
+      const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_Q = tc::uni(tc::smem_u32(tQ));
+      if (tc::elect_one()) {
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::make_idesc(128, 16, 1, 1);
+        const uint64_t db = tc::make_desc(u_Q, 0, 1024);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c)
+          mma_chain(u_tmem + TM_Y + 16 * c, tc::make_desc(u_P + c * kTileBytes, 0, 1024), db, 2048, 2048, kTcPts / 16, idesc, 0);
+        tc::mma_commit(ms.bar_mma);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-      }
-      if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (j * 8 + i < pi.nL) atomicAdd(gw_last + j * 8 + i, acc[i]);
-      }
+      __syncwarp();
     }
+    wait_bar(ms.bar_mma, mma_phase);
+    tc::tc_fence_after();
+    if (q < 2 && hh == 0) {
+      const int o = q * 32 + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v[2];
+        tmem_ld2(tmem + t.lane_addr + TM_Y + 16 * c + 2 * c, v);
+        tc::tmem_ld_wait();
+        acc += v[0] + v[1];
+      }
+      if (o < pi.nL) atomicAdd(gw_last + o, acc);
+    }
+    tc::tc_fence_before();
     __syncthreads();
+    tc::tc_fence_after();
   }
 
   // ---- tensor layers, last to first ------------------------------------------------------------------------------------

@@ -145,51 +145,64 @@ __device__ __forceinline__ void tw_fwd_loop(const LoopW lc, const Chan<N1, N2> c
   for (int c = 0; c < C; ++c) up[c] = u[c];
 }
 
-// tensor layer reverse epilogue: stashed pre-activations (global, prefetched one granule ahead) and output adjoints
-// (TMEM X, or w_last * ubar for the last hidden layer: flag) -> Zbar tiles in P + bias gradient
+// tensor layer reverse epilogue: stashed pre-activations (global; the next 4-column granule is in flight while the
+// current one is processed) and output adjoints (TMEM X, or w_last * ubar for the last hidden layer: flag)
+// -> Zbar tiles in P + bias gradient
 template <int N1, int N2, bool PURE, int AK>
 __device__ __forceinline__ void tw_bwd_loop(const LoopW lc, const Chan<N1, N2> ch, const float* ubp, const float2* zst) {
   constexpr int C = 1 + N1 + N2;
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
-  const int re = (lc.lane >> 4) & 1;
-  const bool rlead = (lc.lane & 15) == 0;
-  float2 zn[C];
+  const int re = reduce4_elem(lc.lane);
+  const bool rlead = (lc.lane & 7) == 0;
+  float2 zn[C][2];
 #pragma unroll
-  for (int c = 0; c < C; ++c) zn[c] = zst[(c * 64 + lc.g0) * kTcPts];
+  for (int c = 0; c < C; ++c) {
+    zn[c][0] = zst[(c * 64 + 2 * lc.g0) * kTcPts];
+    zn[c][1] = zst[(c * 64 + 2 * lc.g0 + 1) * kTcPts];
+  }
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
-    const int ocol = g * 2;
-    float2 zc[C];
+    const int ocol = g * 4;
+    float2 zc[C][2];
 #pragma unroll
-    for (int c = 0; c < C; ++c) zc[c] = zn[c];
+    for (int c = 0; c < C; ++c) { zc[c][0] = zn[c][0]; zc[c][1] = zn[c][1]; }
     if (g + 1 < lc.g1) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) zn[c] = zst[(c * 64 + g + 1) * kTcPts];
+      for (int c = 0; c < C; ++c) {
+        zn[c][0] = zst[(c * 64 + 2 * g + 2) * kTcPts];
+        zn[c][1] = zst[(c * 64 + 2 * g + 3) * kTcPts];
+      }
     }
-    float hb[C][2];
+    float hb[C][4];
     if (!lc.flag) {
 #pragma unroll
-      for (int c = 0; c < C; ++c) tmem_ld2(lc.taddr + c * kTwW + ocol, hb[c]);
+      for (int c = 0; c < C; ++c) tmem_ld4(lc.taddr + c * kTwW + ocol, hb[c]);
       tc::tmem_ld_wait();
     } else {
-      const float w0 = lds_f32(lc.fp + (FW_WL + ocol) * 4), w1 = lds_f32(lc.fp + (FW_WL + ocol + 1) * 4);
 #pragma unroll
-      for (int c = 0; c < C; ++c) { hb[c][0] = w0 * ub[c]; hb[c][1] = w1 * ub[c]; }
+      for (int i = 0; i < 4; ++i) {
+        const float wl = lds_f32(lc.fp + (FW_WL + ocol + i) * 4);
+#pragma unroll
+        for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
+      }
     }
-    P2 zz[C], hv[C], zv[C];
+    float zb0[4];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { zz[c].v = zc[c]; hv[c] = mk2(hb[c][0], hb[c][1]); }
-    chain_bwd<N1, N2, PURE, AK, P2>(lc.act, ch, zz, hv, zv);
-    float zb0[2] = {zv[0].v.x, zv[0].v.y};
-    const float bs = warp_reduce2(zb0, lc.lane);
+    for (int i = 0; i < 4; i += 2) {
+      P2 zz[C], hv[C], zv[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) { zz[c].v = zc[c][i >> 1]; hv[c] = mk2(hb[c][i], hb[c][i + 1]); }
+      chain_bwd<N1, N2, PURE, AK, P2>(lc.act, ch, zz, hv, zv);
+#pragma unroll
+      for (int c = 0; c < C; ++c) { hb[c][i] = zv[c].v.x; hb[c][i + 1] = zv[c].v.y; }
+      zb0[i] = zv[0].v.x; zb0[i + 1] = zv[0].v.y;
+    }
+    const float bs = warp_reduce4(zb0, lc.lane);
     if (rlead) atomicAdd(lc.gb + ocol + re, bs);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float o2[2] = {zv[c].v.x, zv[c].v.y};
-      store_half(tile_of(lc.tP, c, ocol), 0u, lc.p, ocol & 63, o2, false);
-    }
+    for (int c = 0; c < C; ++c) store_half(tile_of(lc.tP, c, ocol), 0u, lc.p, ocol & 63, hb[c], false);
   }
 }
 
@@ -417,51 +430,62 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
         for (int c = 0; c < C; ++c) ub[c] += (tch == c) ? g : 0.f;
       }
   }
-  // ---- last layer: bias and weight gradient on the CUDA cores ----------------------------------------------------------
+  // ---- last layer: bias gradient by warp sums; weight gradient  wbar_last[o] = sum_{c,p} ubar_c[p] H_c^{TL}[p][o]  on the
+  // tensor core: D_c[o][0..15] = H_c^T U with U[p] = (hi, lo) bf16 pairs of ubar_0..ubar_(C-1) (columns 2c, 2c+1) ------------
   {
     float* gb_last = partial + net.b_off[L - 1];
     float* gw_last = partial + net.w_off[L - 1];
     if (hh == 0) {
       const float s = warp_sum<float>(ub[0]);
       if (lane == 0) atomicAdd(gb_last, s);
+      uint32_t w[4];
 #pragma unroll
-      for (int c = 0; c < C; ++c) ms.scratch[c * kTcPts + p] = ub[c];
+      for (int c = 0; c < 4; ++c) w[c] = 0u;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const uint32_t hi = tc::pack_bf16(ub[c], 0.f) & 0xffffu;
+        const float r = ub[c] - __uint_as_float(hi << 16);
+        w[c] = hi | (tc::pack_bf16(r, 0.f) << 16);
+      }
+      const uint32_t q0 = tc::smem_u32(tS);
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + tc::swz_chunk(p, 0)), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(q0 + tc::swz_chunk(p, 1)), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
     }
+    tc::fence_async_smem();
+    tc::tc_fence_before();
     __syncthreads();
-    // wbar_last[o] = sum_{c,p} ubar_c[p] * H_c^{TL}[p][o]; lane <-> (16-byte chunk j of 8 neurons, point sub-group)
-    const int j = lane & 7;
-    const int nbL = (pi.nL + 63) >> 6;
-    for (int kb = 0; kb < nbL; ++kb) {
-      const bool jvalid = kb * 64 + j * 8 < pi.nL;
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int pp = t.warp * 4 + (lane >> 3); pp < kTcPts; pp += (kTcThreads / 32) * 4) {
-#pragma unroll
-        for (int c = 0; c < C; ++c) {
-          uint4 h = make_uint4(0u, 0u, 0u, 0u);
-          if (jvalid) h = *reinterpret_cast<const uint4*>(tP + (c * 2 + kb) * TB + tc::swz_chunk(pp, j));
-          const float uc = ms.scratch[c * kTcPts + pp];
-          const uint32_t w[4] = {h.x, h.y, h.z, h.w};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc[2 * i] = fmaf(uc, __uint_as_float(w[i] << 16), acc[2 * i]);
-            acc[2 * i + 1] = fmaf(uc, __uint_as_float(w[i] & 0xffff0000u), acc[2 * i + 1]);
-          }
-        }
+    if (tc::uni(t.warp) == 0) {
+      const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_S = tc::uni(tc::smem_u32(tS));
+      const int u_nL = tc::uni(pi.nL);
+      if (tc::elect_one()) {
+        tc::tc_fence_after();
+        const uint32_t idesc = tc::make_idesc(128, 16, 1, 1);
+        const uint32_t a_lbo = (u_nL > 64) ? TB : 0u;
+        const uint64_t db = tc::make_desc(u_S, 0, 1024);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c)
+          mma_chain(u_tmem + 16 * c, tc::make_desc(u_P + c * 2 * TB, a_lbo, 1024), db, 2048, 2048, kTcPts / 16, idesc, 0);
+        tc::mma_commit(ms.bar_mma);
       }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
-      }
-      if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (kb * 64 + j * 8 + i < pi.nL) atomicAdd(gw_last + kb * 64 + j * 8 + i, acc[i]);
-      }
+      __syncwarp();
     }
+    wait_bar(ms.bar_mma, mma_phase);
+    tc::tc_fence_after();
+    if (hh == 0) {
+      const int o = q * 32 + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float v[2];
+        tmem_ld2(tmem + t.lane_addr + 16 * c + 2 * c, v);
+        tc::tmem_ld_wait();
+        acc += v[0] + v[1];
+      }
+      if (o < pi.nL) atomicAdd(gw_last + o, acc);
+    }
+    tc::tc_fence_before();
     __syncthreads();
+    tc::tc_fence_after();
   }
 
   // ---- tensor layers, last to first ------------------------------------------------------------------------------------
@@ -483,7 +507,7 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
       __syncwarp();
     }
     {
-      const int ng = n_out / 2;
+      const int ng = n_out / 4;
       LoopW lc;
       lc.fp = tc::smem_u32(fp); lc.bt = lc.fp; lc.tP = tc::smem_u32(tP); lc.gb = gb;
       lc.taddr = tmem + t.lane_addr; lc.act = net.acts[l]; lc.p = p; lc.lane = lane;
