@@ -100,13 +100,13 @@ struct pinn_engine {
   long long buf_elems = 0, stash_per_cta = 0;
   // tensor-core path geometry
   int tile_pts = kTilePts;
-  int tc_split = 0, tc_tl_max = 0, tc_off_P = 0, tc_off_Q = 0, tc_off_misc = 0;
+  int tc_split = 0, tc_tl_max = 0, tc_off_P = 0, tc_off_Q = 0, tc_off_misc = 0, tc_off_ones = 0, tc_mx_dim = 1, tc_mx_taps = 1;
   TcNetSmem tc_nets[PINN_MAX_NETS];
   long long tc_stash_per_cta = 0;
   long long* tc_dbg = nullptr;   // device buffer for pinn_debug_tc_timeline
   // wide tensor path (128-wide layers): streamed weights, fp32 pre-activation stash
   bool tw = false;
-  int tw_off_P = 0, tw_off_S = 0, tw_off_misc = 0, tw_off_fp[PINN_MAX_NETS], tw_wimg[PINN_MAX_NETS];
+  int tw_off_P = 0, tw_off_S = 0, tw_off_misc = 0, tw_off_ones = 0, tw_off_fp[PINN_MAX_NETS], tw_wimg[PINN_MAX_NETS];
   int tw_n_images = 0;
   unsigned char tw_img_net[kTwMaxImages], tw_img_layer[kTwMaxImages];
   long long tw_hstash_per_cta = 0, tw_zstash_per_cta = 0;
@@ -456,6 +456,67 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
     return fail("pinn_create(tc): PINN_MODE_TC_SPLIT supports hidden widths up to 64; 128-wide layers run in "
                 "PINN_MODE_TC_BF16 (or PINN_MODE_FFMA for fp32 accuracy)");
   e->tw = wide;
+  if (wide) {
+    // A network that needs more than kTwMaxC channels is evaluated in several passes ("slots") over the same weights,
+    // each with the value channel and a subset of the derivative directions (first-fit over the directions, a
+    // direction with a pure second derivative costs 2 channels).  The passes recompute the value channel; the
+    // gradient contributions add up in the per-CTA partial.
+    for (int t = 0; t < d->n_terms; ++t) {
+      DevTerm& T = P.terms[t];
+      bool need = false;
+      for (int s2 = 0; s2 < T.n_used; ++s2) need = need || T.chan[s2].C > kTwMaxC;
+      if (!need) continue;
+      int n_new = 0, new_net[PINN_MAX_NETS], first_new[PINN_MAX_NETS];
+      DevChan nch[PINN_MAX_NETS];
+      int dir_slot[PINN_MAX_NETS][PINN_MAX_IN], dir_pos[PINN_MAX_NETS][PINN_MAX_IN];
+      for (int s2 = 0; s2 < T.n_used; ++s2) {
+        const DevChan& ch = T.chan[s2];
+        first_new[s2] = n_new;
+        if (ch.C <= kTwMaxC) {
+          if (n_new >= PINN_MAX_NETS) return fail("pinn_create(tc): term %d needs more than %d network passes", t, PINN_MAX_NETS);
+          for (int j = 0; j < ch.n1; ++j) { dir_slot[s2][j] = n_new; dir_pos[s2][j] = j; }
+          new_net[n_new] = T.used_net[s2]; nch[n_new] = ch; ++n_new;
+          continue;
+        }
+        if (!ch.pure)
+          return fail("pinn_create(tc): term %d needs %d channels including mixed second derivatives; the 128-wide tcgen05 "
+                      "path splits only pure second derivatives into passes (use PINN_MODE_FFMA)", t, ch.C);
+        bool placed[PINN_MAX_IN] = {false};
+        int left = ch.n1;
+        while (left > 0) {
+          if (n_new >= PINN_MAX_NETS) return fail("pinn_create(tc): term %d needs more than %d network passes", t, PINN_MAX_NETS);
+          DevChan g;
+          memset(&g, 0, sizeof g);
+          for (int j = 0; j < PINN_MAX_IN; ++j) g.rows[j] = ch.rows[j];
+          int cost = 0;
+          for (int j = 0; j < ch.n1; ++j) {          // pure directions (cost 2) come first in the canonical order
+            const int cj = 1 + (j < ch.n2 ? 1 : 0);
+            if (placed[j] || cost + cj > kTwMaxC - 1) continue;
+            placed[j] = true; --left; cost += cj;
+            dir_slot[s2][j] = n_new; dir_pos[s2][j] = g.n1;
+            g.dir1[g.n1++] = ch.dir1[j];
+            if (j < ch.n2) ++g.n2;
+          }
+          for (int q2 = 0; q2 < g.n2; ++q2) g.s_a[q2] = g.s_b[q2] = q2;
+          g.pure = 1; g.C = 1 + g.n1 + g.n2;
+          new_net[n_new] = T.used_net[s2]; nch[n_new] = g; ++n_new;
+        }
+      }
+      for (int i = 0; i < T.n_taps; ++i) {
+        const int os = T.tap_slot[i], tch = T.tap_ch[i];
+        const DevChan& ch = T.chan[os];
+        if (tch == 0) { T.tap_slot[i] = first_new[os]; T.tap_ch[i] = 0; }
+        else if (tch <= ch.n1) { T.tap_slot[i] = dir_slot[os][tch - 1]; T.tap_ch[i] = 1 + dir_pos[os][tch - 1]; }
+        else {
+          const int q2 = tch - 1 - ch.n1;          // pure: second-derivative channel q2 belongs to direction q2
+          const int ns = dir_slot[os][q2];
+          T.tap_slot[i] = ns; T.tap_ch[i] = 1 + nch[ns].n1 + dir_pos[os][q2];
+        }
+      }
+      T.n_used = n_new;
+      for (int s2 = 0; s2 < n_new; ++s2) { T.used_net[s2] = new_net[s2]; T.chan[s2] = nch[s2]; }
+    }
+  }
   int n_used_max = 1;
   for (int t = 0; t < d->n_terms; ++t) {
     const DevTerm& T = P.terms[t];
@@ -478,16 +539,19 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       if (T.tap_out[i] != 0) return fail("pinn_create(tc): term %d tap %d: output component must be 0", t, i);
   }
   e->tc_tl_max = tl_max;
+  e->tc_mx_dim = 1; e->tc_mx_taps = 1;
+  for (int t = 0; t < d->n_terms; ++t) {
+    e->tc_mx_dim = std::max(e->tc_mx_dim, (int)P.terms[t].dim);
+    e->tc_mx_taps = std::max(e->tc_mx_taps, (int)P.terms[t].n_taps);
+  }
   if (wide) {
-    for (int t = 0; t < d->n_terms; ++t)
-      if (P.terms[t].n_used > 1)
-        return fail("pinn_create(tc): term %d couples %d networks; the 128-wide tcgen05 path handles one network per "
-                    "term (use PINN_MODE_FFMA)", t, P.terms[t].n_used);
     int maxCw = 1;
-    for (int t = 0; t < d->n_terms; ++t) maxCw = std::max(maxCw, (int)P.terms[t].chan[0].C);
+    for (int t = 0; t < d->n_terms; ++t)
+      for (int s2 = 0; s2 < P.terms[t].n_used; ++s2) maxCw = std::max(maxCw, (int)P.terms[t].chan[s2].C);
     size_t o2 = 0;
     e->tw_off_P = (int)o2; o2 += (size_t)maxCw * kTwNB * kTileBytes;
     e->tw_off_S = (int)o2; o2 += (size_t)2 * kTwImgBytes;
+    e->tw_off_ones = (int)o2; o2 += 1024;
     e->tw_n_images = 0;
     for (int k = 0; k < PINN_MAX_NETS; ++k) { e->tw_off_fp[k] = -1; e->tw_wimg[k] = 0; }
     for (int k = 0; k < d->n_nets; ++k) {
@@ -501,13 +565,14 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       }
     }
     e->tw_off_misc = (int)o2;
-    o2 += tc_misc_bytes();
+    o2 += tc_misc_bytes(e->tc_mx_dim, e->tc_mx_taps);
     if (o2 + 1024 > (size_t)max_smem)
       return fail("pinn_create(tc): the problem needs %zu bytes of shared memory per CTA (limit %d): too many networks "
                   "for the 128-wide tcgen05 path", o2, max_smem);
     e->smem = o2;
-    e->tw_hstash_per_cta = (long long)tl_max * kTwMaxC * kTwNB * kTileBytes;
-    e->tw_zstash_per_cta = (long long)tl_max * kTwMaxC * 64 * kTcPts * 2;      // floats
+    // per pass: inputs of the tl_max tensor layers + the last hidden activations (restored for multi-pass terms)
+    e->tw_hstash_per_cta = (long long)n_used_max * (tl_max + 1) * kTwMaxC * kTwNB * kTileBytes;
+    e->tw_zstash_per_cta = (long long)n_used_max * tl_max * kTwMaxC * 64 * kTcPts * 2;      // floats
     e->tc_stash_per_cta = e->tw_hstash_per_cta;
     return 0;
   }
@@ -526,12 +591,13 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       else e->tc_nets[k].w_lo[l] = e->tc_nets[k].w_hi[l];
     }
   }
+  e->tc_off_ones = (int)off; off += 1024;      // 1024-aligned: P, Q and the weight tiles are multiples of 8 KB
   for (int k = 0; k < d->n_nets; ++k) {
     e->tc_nets[k].fp = (int)off;
     off += ((size_t)FP_SIZE * 4 + 15) & ~size_t(15);
   }
   e->tc_off_misc = (int)off;
-  off += tc_misc_bytes();
+  off += tc_misc_bytes(e->tc_mx_dim, e->tc_mx_taps);
   if (off + 1024 > (size_t)max_smem)   // + the kernel's static shared memory
     return fail("pinn_create(tc): the problem needs %zu bytes of shared memory per CTA (limit %d): too many "
                 "resident weight tiles / channels for the tcgen05 path", off, max_smem);
@@ -731,7 +797,7 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
     w.wpack = (const uint8_t*)e->tw_wpack; w.tl_max = std::max(e->tc_tl_max, 1);
     w.tile_begin = a.tile_begin; w.tile_end = a.tile_end; w.mode = a.mode; w.resid_out = (float*)a.resid_out;
     w.dbg = e->tc_dbg;
-    w.off_P = e->tw_off_P; w.off_S = e->tw_off_S; w.off_misc = e->tw_off_misc;
+    w.off_P = e->tw_off_P; w.off_S = e->tw_off_S; w.off_misc = e->tw_off_misc; w.off_ones = e->tw_off_ones; w.mx_dim = e->tc_mx_dim; w.mx_taps = e->tc_mx_taps;
     for (int k = 0; k < PINN_MAX_NETS; ++k) {
       w.off_fp[k] = e->tw_off_fp[k]; w.wimg[k] = e->tw_wimg[k];
       int ak = 1;
@@ -750,7 +816,7 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
   t.prob = a.prob; t.theta = (const float*)a.theta; t.partial = (float*)a.partial; t.term_sums = a.term_sums;
   t.stash = (uint8_t*)e->stash; t.stash_per_cta = e->tc_stash_per_cta; t.split = e->tc_split; t.tl_max = std::max(e->tc_tl_max, 1);
   t.tile_begin = a.tile_begin; t.tile_end = a.tile_end; t.mode = a.mode; t.resid_out = (float*)a.resid_out;
-  t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc;
+  t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc; t.off_ones = e->tc_off_ones; t.mx_dim = e->tc_mx_dim; t.mx_taps = e->tc_mx_taps;
   t.dbg = e->tc_dbg;
   t.off_Q_bytes = e->tc_off_Q - e->tc_off_P;   // P and Q regions have the same size
   for (int k = 0; k < PINN_MAX_NETS; ++k) {

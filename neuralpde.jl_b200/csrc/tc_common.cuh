@@ -269,19 +269,19 @@ __device__ __forceinline__ void dbg_mark(CS* cs, int id) {
 }
 
 struct Misc {   // carve-up of the misc region
-  float *Xs, *taps, *tapbar, *scratch, *qws, *rres;
+  float *Xs, *taps, *tapbar, *scratch, *qws;
   double* tsum;
   uint64_t *bar_mma, *bar_ld;
   uint32_t* tmem_slot;
 };
-__device__ __forceinline__ Misc misc_of(uint8_t* m) {
+// mx_dim / mx_taps: largest point dimension / tap count over the problem's terms (the arrays are sized to them)
+__device__ __forceinline__ Misc misc_of(uint8_t* m, int mx_dim, int mx_taps) {
   Misc r;
-  r.Xs = reinterpret_cast<float*>(m);             m += PINN_MAX_DIM * kTcPts * 4;
-  r.taps = reinterpret_cast<float*>(m);           m += kTcMaxTaps * kTcPts * 4;
-  r.tapbar = reinterpret_cast<float*>(m);         m += kTcMaxTaps * kTcPts * 4;
+  r.Xs = reinterpret_cast<float*>(m);             m += mx_dim * kTcPts * 4;
+  r.taps = reinterpret_cast<float*>(m);           m += mx_taps * kTcPts * 4;
+  r.tapbar = reinterpret_cast<float*>(m);         m += mx_taps * kTcPts * 4;
   r.scratch = reinterpret_cast<float*>(m);        m += kTcMaxC * kTcPts * 4;
   r.qws = reinterpret_cast<float*>(m);            m += kTcPts * 4;
-  r.rres = reinterpret_cast<float*>(m);           m += kTcPts * 4;
   r.tsum = reinterpret_cast<double*>(m);          m += PINN_MAX_TERMS * 8;
   r.bar_mma = reinterpret_cast<uint64_t*>(m);     m += 8;
   r.bar_ld = reinterpret_cast<uint64_t*>(m);      m += 8;

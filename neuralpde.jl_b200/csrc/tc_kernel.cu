@@ -27,7 +27,7 @@ namespace pinn {
 // drag a context struct through local memory
 struct CtaShared {
   uint32_t tmem;
-  int split, tl_max, off_P, off_Q, off_misc;
+  int split, tl_max, off_P, off_Q, off_misc, off_ones, mx_dim, mx_taps;
   float* partial;
   uint8_t* stash;
   const float* theta;
@@ -145,15 +145,14 @@ __device__ __forceinline__ void tl_fwd_loop(const LoopCtx lc, const Chan<N1, N2>
 }
 
 // tensor layer backward epilogue for the column group starting at c0: recomputed Z (TMEM Y) and output
-// adjoints (TMEM X, or w_last * ubar for the last hidden layer: flag) -> Zbar tiles + bias gradient
+// adjoints (TMEM X, or w_last * ubar for the last hidden layer: flag) -> Zbar tiles (the bias gradient is a
+// column sum of Zbar_0, taken by one MMA chain against the constant ones atom in net_backward)
 template <int N1, int N2, bool PURE, int AK>
 __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2> ch, const float* ubp) {
   constexpr int C = 1 + N1 + N2;
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
-  const int re = GWB == 4 ? reduce4_elem(lc.lane) : ((lc.lane >> 4) & 1);
-  const bool rlead = GWB == 4 ? ((lc.lane & 7) == 0) : ((lc.lane & 15) == 0);
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
     const int ocol = lc.c0 + g * GWB;
@@ -173,7 +172,6 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
         for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
       }
     }
-    float zb0[GWB];
 #pragma unroll
     for (int i = 0; i < GWB; i += 2) {
       P2 zz[C], hv[C], zv[C];
@@ -185,10 +183,7 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
       chain_bwd<N1, N2, PURE, AK, P2>(lc.act, ch, zz, hv, zv);
 #pragma unroll
       for (int c = 0; c < C; ++c) { hb[c][i] = zv[c].v.x; hb[c][i + 1] = zv[c].v.y; }
-      zb0[i] = zv[0].v.x; zb0[i + 1] = zv[0].v.y;
     }
-    const float bs = warp_reduceg(zb0, lc.lane);
-    if (rlead) atomicAdd(lc.gb + ocol + re, bs);
 #pragma unroll
     for (int c = 0; c < C; ++c) store_half(lc.tP + c * kTileBytes, lc.tP, lc.p, ocol, hb[c], false);
   }
@@ -303,7 +298,7 @@ __device__ __noinline__ uint32_t net_forward(CtaShared* cs, const DevProblem* Pp
   const float* fp = reinterpret_cast<const float*>(smem + ns.fp);
   uint8_t* tP = smem + cs->off_P;
   uint8_t* tQ = smem + cs->off_Q;
-  const Misc ms = misc_of(smem + cs->off_misc);
+  const Misc ms = misc_of(smem + cs->off_misc, cs->mx_dim, cs->mx_taps);
   const uint32_t tmem = cs->tmem;
   const bool split = cs->split != 0;
   PassInfo<N1, N2> pi;
@@ -431,7 +426,7 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
   const float* fp = reinterpret_cast<const float*>(smem + ns.fp);
   uint8_t* tP = smem + cs->off_P;
   uint8_t* tQ = smem + cs->off_Q;
-  const Misc ms = misc_of(smem + cs->off_misc);
+  const Misc ms = misc_of(smem + cs->off_misc, cs->mx_dim, cs->mx_taps);
   const uint32_t tmem = cs->tmem;
   float* partial = cs->partial;
   PassInfo<N1, N2> pi;
@@ -577,6 +572,7 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
     dbg_mark(cs, 26);
     if (tc::uni(t.warp) == 0) {
       const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_Q = tc::uni(tc::smem_u32(tQ)), u_w = tc::uni(whi);
+      const uint32_t u_ones = tc::uni(tc::smem_u32(smem + cs->off_ones));
       const int u_nin = tc::uni(n_in), u_nko = tc::uni(n_out / 16);
       if (tc::elect_one()) {
         tc::tc_fence_after();
@@ -592,6 +588,9 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
         for (int c = 0; c < C; ++c)
           mma_chain(u_tmem + TM_Y, tc::make_desc(u_P + c * kTileBytes, 0, 1024), tc::make_desc(u_Q + c * kTileBytes, 0, 1024),
                     2048, 2048, kTcPts / 16, iwg, c > 0 ? 1u : 0u);
+        // bias gradient: bbar_l[o] = sum_p Zbar_0[p][o] -> Y column 64 (B = the constant ones atom, SBO = 0, no k advance)
+        mma_chain(u_tmem + TM_Y + 64, tc::make_desc(u_P, 0, 1024), tc::make_desc(u_ones, 0, 0), 2048, 0, kTcPts / 16,
+                  tc::make_idesc(128, 16, 1, 1), 0);
         tc::mma_commit(ms.bar_mma);
       }
       __syncwarp();
@@ -603,6 +602,12 @@ __device__ __noinline__ uint32_t net_backward(CtaShared* cs, const DevProblem* P
     // flush the weight-gradient tile: TMEM lane = output neuron o, column = input neuron k
     if (q < 2) {
       const int o = q * 32 + lane;
+      if (hh == 0) {
+        float v[2];
+        tmem_ld2(tmem + t.lane_addr + TM_Y + 64, v);
+        tc::tmem_ld_wait();
+        if (o < n_out) atomicAdd(gb + o, v[0]);
+      }
       const int part = n_in / kNH;
 #pragma unroll 1
       for (int k0 = hh * part; k0 < (hh + 1) * part; k0 += 4) {
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const DevProblem* Pp = args.prob;
   const DevProblem& P = *Pp;
-  const Misc ms = misc_of(smem + args.off_misc);
+  const Misc ms = misc_of(smem + args.off_misc, args.mx_dim, args.mx_taps);
   float* partial = args.partial + (long long)blockIdx.x * P.n_theta;
   const bool want_grad = (args.mode == 0);
   const float* theta = args.theta;
@@ -734,7 +739,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     tc::mbar_init(ms.bar_ld, 1);
     tc::fence_barrier_init();
     cs.split = args.split; cs.tl_max = args.tl_max; cs.off_P = args.off_P; cs.off_Q = args.off_Q;
-    cs.off_misc = args.off_misc; cs.partial = partial;
+    cs.off_misc = args.off_misc; cs.off_ones = args.off_ones; cs.mx_dim = args.mx_dim; cs.mx_taps = args.mx_taps;
+    cs.partial = partial;
     cs.stash = args.stash + (long long)blockIdx.x * args.stash_per_cta;
     cs.theta = theta;
     cs.dbg = (blockIdx.x == 0) ? args.dbg : nullptr;
@@ -754,6 +760,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     }
   }
   if (tid < PINN_MAX_TERMS) ms.tsum[tid] = 0.0;
+  if (tid < 64) {      // ones atom: row r (128 B) holds bf16 1.0 in logical column 0 = 16-byte chunk (0 ^ r)
+    const int r = tid >> 3, ch = tid & 7;
+    *reinterpret_cast<uint4*>(smem + args.off_ones + r * 128 + ch * 16) = make_uint4(ch == r ? 0x00003f80u : 0u, 0u, 0u, 0u);
+  }
   // stage weights: bf16 hi / lo operand tiles of the tensor layers, fp32 blocks of the first / last layers
   for (int kn = 0; kn < P.n_nets; ++kn) {
     const DevNet& net = P.nets[kn];
@@ -930,9 +940,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------
-size_t tc_misc_bytes() {
-  return (size_t)PINN_MAX_DIM * kTcPts * 4 + 2 * (size_t)kTcMaxTaps * kTcPts * 4 + (size_t)kTcMaxC * kTcPts * 4 +
-         2 * kTcPts * 4 + PINN_MAX_TERMS * 8 + 16 + 16;
+size_t tc_misc_bytes(int mx_dim, int mx_taps) {
+  return (size_t)mx_dim * kTcPts * 4 + 2 * (size_t)mx_taps * kTcPts * 4 + (size_t)kTcMaxC * kTcPts * 4 + kTcPts * 4 +
+         PINN_MAX_TERMS * 8 + 16 + 16;
 }
 
 cudaError_t tc_launch(const TcArgs& a, int grid, size_t smem, cudaStream_t st) {

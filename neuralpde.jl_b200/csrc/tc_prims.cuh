@@ -148,6 +148,7 @@ __device__ __forceinline__ uint32_t uni(uint32_t v) { return __shfl_sync(0xfffff
 __device__ __forceinline__ int uni(int v) { return __shfl_sync(0xffffffffu, v, 0); }
 __device__ __forceinline__ uint64_t uni(uint64_t v) { return __shfl_sync(0xffffffffu, (unsigned long long)v, 0); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---- descriptors ---------------------------------------------------------------------------------------
 // shared-memory matrix descriptor, 128-byte swizzle, sm_100 version field = 1

@@ -47,6 +47,8 @@ struct TcArgs {
   long long* dbg;         // optional: 1000 x int64 phase timestamps of CTA 0 (pinn_debug_tc_timeline)
   int off_P, off_Q, off_misc;   // byte offsets into dynamic shared memory
   int off_Q_bytes;              // size of the Q tile region
+  int off_ones;                 // 1 KB constant atom: bf16 1.0 in column 0 of 8 swizzled rows (bias gradient by MMA)
+  int mx_dim, mx_taps;          // sizes of the per-tile coordinate / tap arrays in the misc region
   TcNetSmem nets[PINN_MAX_NETS];
   int net_ak[PINN_MAX_NETS];   // 1: every hidden activation is tanh (fast path), 0: generic
   double seed[PINN_MAX_TERMS];
@@ -85,6 +87,8 @@ struct TwArgs {
   float* resid_out;
   long long* dbg;
   int off_P, off_S, off_misc;       // byte offsets into dynamic shared memory (P: C x 2 tiles, S: 2 x 32 KB)
+  int off_ones;                     // 1 KB constant atom (bias gradient by MMA)
+  int mx_dim, mx_taps;              // sizes of the per-tile coordinate / tap arrays in the misc region
   int off_fp[PINN_MAX_NETS];        // fp32 parameter block per network (-1: unused)
   int net_ak[PINN_MAX_NETS];
   double seed[PINN_MAX_TERMS];
@@ -102,7 +106,7 @@ struct TwPackArgs {
 cudaError_t tw_pack_launch(const TwPackArgs& a, cudaStream_t st);
 cudaError_t tw_launch(const TwArgs& a, int grid, size_t smem, cudaStream_t st);
 
-size_t tc_misc_bytes();
+size_t tc_misc_bytes(int mx_dim, int mx_taps);
 cudaError_t tc_launch(const TcArgs& a, int grid, size_t smem, cudaStream_t st);
 
 }  // namespace pinn

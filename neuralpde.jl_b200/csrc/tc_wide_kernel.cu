@@ -30,7 +30,7 @@ constexpr uint32_t TB = kTileBytes;
 
 struct TwShared {
   uint32_t tmem;
-  int tl_max, off_P, off_S, off_misc;
+  int tl_max, off_P, off_S, off_misc, off_ones, mx_dim, mx_taps;
   float* partial;
   uint8_t* hstash;
   float* zstash;
@@ -145,36 +145,26 @@ __device__ __forceinline__ void tw_fwd_loop(const LoopW lc, const Chan<N1, N2> c
   for (int c = 0; c < C; ++c) up[c] = u[c];
 }
 
-// tensor layer reverse epilogue: stashed pre-activations (global; the next 4-column granule is in flight while the
-// current one is processed) and output adjoints (TMEM X, or w_last * ubar for the last hidden layer: flag)
-// -> Zbar tiles in P + bias gradient
+// tensor layer reverse epilogue: stashed pre-activations and output adjoints (TMEM X, or w_last * ubar for the last
+// hidden layer: flag) -> Zbar tiles in P (the bias gradient is a column sum of Zbar_0, taken by an MMA chain against
+// the ones atom).  The stash is read from HBM more often than from L2 (148 CTAs x 1.5 MB in flight > L2), so the loads
+// of two 4-column granules are kept in flight per thread (two register buffers used alternately).
 template <int N1, int N2, bool PURE, int AK>
 __device__ __forceinline__ void tw_bwd_loop(const LoopW lc, const Chan<N1, N2> ch, const float* ubp, const float2* zst) {
   constexpr int C = 1 + N1 + N2;
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
-  const int re = reduce4_elem(lc.lane);
-  const bool rlead = (lc.lane & 7) == 0;
-  float2 zn[C][2];
+  float2 za[C][2], zb[C][2];
+  auto load = [&](float2 (&zz)[C][2], int g) {
 #pragma unroll
-  for (int c = 0; c < C; ++c) {
-    zn[c][0] = zst[(c * 64 + 2 * lc.g0) * kTcPts];
-    zn[c][1] = zst[(c * 64 + 2 * lc.g0 + 1) * kTcPts];
-  }
-#pragma unroll 1
-  for (int g = lc.g0; g < lc.g1; ++g) {
-    const int ocol = g * 4;
-    float2 zc[C][2];
-#pragma unroll
-    for (int c = 0; c < C; ++c) { zc[c][0] = zn[c][0]; zc[c][1] = zn[c][1]; }
-    if (g + 1 < lc.g1) {
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        zn[c][0] = zst[(c * 64 + 2 * g + 2) * kTcPts];
-        zn[c][1] = zst[(c * 64 + 2 * g + 3) * kTcPts];
-      }
+    for (int c = 0; c < C; ++c) {
+      zz[c][0] = zst[(c * 64 + 2 * g) * kTcPts];
+      zz[c][1] = zst[(c * 64 + 2 * g + 1) * kTcPts];
     }
+  };
+  auto process = [&](const float2 (&zc)[C][2], int g) {
+    const int ocol = g * 4;
     float hb[C][4];
     if (!lc.flag) {
 #pragma unroll
@@ -188,7 +178,6 @@ __device__ __forceinline__ void tw_bwd_loop(const LoopW lc, const Chan<N1, N2> c
         for (int c = 0; c < C; ++c) hb[c][i] = wl * ub[c];
       }
     }
-    float zb0[4];
 #pragma unroll
     for (int i = 0; i < 4; i += 2) {
       P2 zz[C], hv[C], zv[C];
@@ -197,12 +186,20 @@ __device__ __forceinline__ void tw_bwd_loop(const LoopW lc, const Chan<N1, N2> c
       chain_bwd<N1, N2, PURE, AK, P2>(lc.act, ch, zz, hv, zv);
 #pragma unroll
       for (int c = 0; c < C; ++c) { hb[c][i] = zv[c].v.x; hb[c][i + 1] = zv[c].v.y; }
-      zb0[i] = zv[0].v.x; zb0[i + 1] = zv[0].v.y;
     }
-    const float bs = warp_reduce4(zb0, lc.lane);
-    if (rlead) atomicAdd(lc.gb + ocol + re, bs);
 #pragma unroll
     for (int c = 0; c < C; ++c) store_half(tile_of(lc.tP, c, ocol), 0u, lc.p, ocol & 63, hb[c], false);
+  };
+  load(za, lc.g0);
+  if (lc.g0 + 1 < lc.g1) load(zb, lc.g0 + 1);
+#pragma unroll 1
+  for (int g = lc.g0; g < lc.g1; g += 2) {
+    process(za, g);
+    if (g + 2 < lc.g1) load(za, g + 2);
+    if (g + 1 < lc.g1) {
+      process(zb, g + 1);
+      if (g + 3 < lc.g1) load(zb, g + 3);
+    }
   }
 }
 
@@ -264,7 +261,7 @@ __device__ __noinline__ uint32_t tw_net_forward(TwShared* cs, const DevProblem* 
   const float* fp = reinterpret_cast<const float*>(smem + cs->off_fp[net_id]);
   uint8_t* tP = smem + cs->off_P;
   uint8_t* tS = smem + cs->off_S;
-  const Misc ms = misc_of(smem + cs->off_misc);
+  const Misc ms = misc_of(smem + cs->off_misc, cs->mx_dim, cs->mx_taps);
   const uint32_t tmem = cs->tmem;
   PassInfo<N1, N2> pi;
   load_pass<N1, N2>(pi, net, dc);
@@ -274,7 +271,7 @@ __device__ __noinline__ uint32_t tw_net_forward(TwShared* cs, const DevProblem* 
   float x[PINN_MAX_IN];
 #pragma unroll
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < pi.d_in) ? ms.Xs[dc.rows[k] * kTcPts + p] : 0.f;
-  uint8_t* hst = cs->hstash + (size_t)slot * cs->tl_max * kTwMaxC * 2 * TB;
+  uint8_t* hst = cs->hstash + (size_t)slot * (cs->tl_max + 1) * kTwMaxC * 2 * TB;
   float* zst = cs->zstash + (size_t)slot * cs->tl_max * kTwMaxC * 64 * kTcPts * 2;
   const uint8_t* wimg = cs->wpack + (size_t)cs->wimg[net_id] * kTwImgBytes;
 
@@ -363,6 +360,25 @@ __device__ __noinline__ uint32_t tw_net_forward(TwShared* cs, const DevProblem* 
     tw_fwd_loop<N1, N2, PURE, AK>(lc, pi.ch, u, zl);
   }
   // ---- last layer (n -> 1, identity): combine the column parts of every point ---------------------------------
+  if (want_grad && tm.n_used > 1) {
+    // several passes share P: keep this pass's last hidden activations for its reverse sweep
+    tc::fence_async_smem();
+    __syncthreads();
+    if (tc::uni(t.warp) == 0) {
+      const uint32_t u_P = tc::uni(tc::smem_u32(tP));
+      const uint64_t u_hst = tc::uni((uint64_t)(hst + (size_t)TL * kTwMaxC * 2 * TB));
+      const int u_nb = tc::uni((pi.nL + 63) >> 6);
+      if (tc::elect_one()) {
+#pragma unroll 1
+        for (int c = 0; c < C; ++c)
+          for (int kb = 0; kb < u_nb; ++kb)
+            tc::bulk_store_u((void*)(u_hst + (uint64_t)(c * 2 + kb) * TB), u_P + (c * 2 + kb) * TB, TB);
+        tc::bulk_commit();
+        tc::bulk_wait_read0();
+      }
+      __syncwarp();
+    }
+  }
   __syncthreads();
   dbg_mark(cs, 15);
 #pragma unroll
@@ -394,6 +410,9 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int C = 1 + N1 + N2;
   constexpr uint32_t WG = (C <= 3) ? 384u : 0u;       // TMEM column of the weight-gradient accumulator
+  constexpr uint32_t BC = (C <= 2) ? 256u : 128u;     // TMEM column of the bias-gradient column sums (16 columns)
+  // dgrad channels whose TMEM columns hold the weight / bias gradient until it is flushed: issued after the flush
+  constexpr uint32_t DEFER = (C == 4) ? 0x3u : ((C == 3) ? 0x2u : 0x0u);
   const DevTerm& tm = *tmp;
   const int net_id = tm.used_net[slot];
   const DevNet& net = Pp->nets[net_id];
@@ -401,7 +420,7 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
   const float* fp = reinterpret_cast<const float*>(smem + cs->off_fp[net_id]);
   uint8_t* tP = smem + cs->off_P;
   uint8_t* tS = smem + cs->off_S;
-  const Misc ms = misc_of(smem + cs->off_misc);
+  const Misc ms = misc_of(smem + cs->off_misc, cs->mx_dim, cs->mx_taps);
   const uint32_t tmem = cs->tmem;
   float* partial = cs->partial;
   PassInfo<N1, N2> pi;
@@ -412,11 +431,30 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
   float x[PINN_MAX_IN];
 #pragma unroll
   for (int k = 0; k < PINN_MAX_IN; ++k) x[k] = (k < pi.d_in) ? ms.Xs[dc.rows[k] * kTcPts + p] : 0.f;
-  uint8_t* hst = cs->hstash + (size_t)slot * cs->tl_max * kTwMaxC * 2 * TB;
+  uint8_t* hst = cs->hstash + (size_t)slot * (cs->tl_max + 1) * kTwMaxC * 2 * TB;
   const float* zst = cs->zstash + (size_t)slot * cs->tl_max * kTwMaxC * 64 * kTcPts * 2;
   const uint8_t* wimg = cs->wpack + (size_t)cs->wimg[net_id] * kTwImgBytes;
 
   dbg_mark(cs, 20);
+  if (tm.n_used > 1) {
+    // restore this pass's last hidden activations into P
+    if (tc::uni(t.warp) == 0) {
+      const uint32_t u_P = tc::uni(tc::smem_u32(tP));
+      const uint64_t u_hst = tc::uni((uint64_t)(hst + (size_t)TL * kTwMaxC * 2 * TB));
+      const int u_nb = tc::uni((pi.nL + 63) >> 6);
+      if (tc::elect_one()) {
+        tc::fence_async_smem();
+        tc::mbar_arrive_expect_tx(&cs->bar_ld[0], (uint32_t)(C * u_nb) * TB);
+#pragma unroll 1
+        for (int c = 0; c < C; ++c)
+          for (int kb = 0; kb < u_nb; ++kb)
+            tc::bulk_load_u(u_P + (c * 2 + kb) * TB, (const void*)(u_hst + (uint64_t)(c * 2 + kb) * TB), TB, tc::smem_u32(&cs->bar_ld[0]));
+        tw_wait_ld(cs, 0);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+  }
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = 0.f;
@@ -523,6 +561,7 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
     if (tc::uni(t.warp) == 0) {
       const uint32_t u_tmem = tc::uni(tmem), u_P = tc::uni(tc::smem_u32(tP)), u_S = tc::uni(tc::smem_u32(tS));
       const int u_nin = tc::uni(n_in), u_nout = tc::uni(n_out), u_l = tc::uni(l);
+      const uint32_t u_ones = tc::uni(tc::smem_u32(smem + cs->off_ones));
       const uint64_t u_hst = tc::uni((uint64_t)(hst + (size_t)(l - 1) * kTwMaxC * 2 * TB));
       const uint64_t u_w = tc::uni((uint64_t)wimg);
       if (tc::elect_one()) {
@@ -551,6 +590,9 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
             tw_load(cs, b, u_S + b * kTwImgBytes, (const uint8_t*)u_w + (size_t)(u_l - 1) * kTwImgBytes, nb_in);
           }
         }
+        // bias gradient: bbar_l[o] = sum_p Zbar_0[p][o]  (B = the constant ones atom: SBO = 0, no k advance)
+        mma_chain(u_tmem + BC, tc::make_desc(u_P, a_lbo, 1024), tc::make_desc(u_ones, 0, 0), 2048, 0, kTcPts / 16,
+                  tc::make_idesc(128, 16, 1, 1), 0);
         if (pend0) tw_wait_free(cs, 0);
         if (pend1) tw_wait_free(cs, 1);
         tc::mma_commit(ms.bar_mma);
@@ -572,20 +614,28 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
         const uint32_t idg = tc::make_idesc(128, u_nin, 0, 1);
         const uint32_t wbuf = u_S + wb * kTwImgBytes;
 #pragma unroll 1
-        for (int c = C - 1; c >= (C == 4 ? 1 : 0); --c)
+        for (int c = C - 1; c >= 0; --c) {
+          if ((DEFER >> c) & 1u) continue;
 #pragma unroll 1
           for (int ob = 0; ob < nb_out; ++ob) {
             const int nk = ((u_nout - ob * 64) < 64 ? (u_nout - ob * 64) : 64) >> 4;
             mma_chain(u_tmem + c * kTwW, tc::make_desc(u_P + (c * 2 + ob) * TB, 0, 1024), tc::make_desc(wbuf + ob * 8192, TB, 1024),
                       32, 2048, nk, idg, ob > 0 ? 1u : 0u);
           }
-        if (C != 4) tc::mma_commit(ms.bar_mma);
+        }
+        if (DEFER == 0) tc::mma_commit(ms.bar_mma);
       }
       __syncwarp();
     }
     // flush the weight-gradient accumulator: TMEM lane = output neuron o, column = input neuron k
     {
       const int o = q * 32 + lane;
+      if (hh == 0) {
+        float v[2];
+        tmem_ld2(tmem + t.lane_addr + BC, v);
+        tc::tmem_ld_wait();
+        if (o < n_out) atomicAdd(gb + o, v[0]);
+      }
       const int part = n_in / kNH;
 #pragma unroll 1
       for (int k0 = hh * part; k0 < (hh + 1) * part; k0 += 4) {
@@ -598,8 +648,8 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
         }
       }
     }
-    if (C == 4) {
-      // channel 0's adjoints land on the columns the weight gradient just left
+    if (DEFER != 0) {
+      // the remaining channels' adjoints land on the columns the weight / bias gradient just left
       tc::tc_fence_before();
       __syncthreads();
       if (tc::uni(t.warp) == 0) {
@@ -611,10 +661,14 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
           const uint32_t idg = tc::make_idesc(128, u_nin, 0, 1);
           const uint32_t wbuf = u_S + wb * kTwImgBytes;
 #pragma unroll 1
-          for (int ob = 0; ob < nb_out; ++ob) {
-            const int nk = ((u_nout - ob * 64) < 64 ? (u_nout - ob * 64) : 64) >> 4;
-            mma_chain(u_tmem, tc::make_desc(u_P + ob * TB, 0, 1024), tc::make_desc(wbuf + ob * 8192, TB, 1024), 32, 2048, nk, idg,
-                      ob > 0 ? 1u : 0u);
+          for (int c = C - 1; c >= 0; --c) {
+            if (!((DEFER >> c) & 1u)) continue;
+#pragma unroll 1
+            for (int ob = 0; ob < nb_out; ++ob) {
+              const int nk = ((u_nout - ob * 64) < 64 ? (u_nout - ob * 64) : 64) >> 4;
+              mma_chain(u_tmem + c * kTwW, tc::make_desc(u_P + (c * 2 + ob) * TB, 0, 1024),
+                        tc::make_desc(wbuf + ob * 8192, TB, 1024), 32, 2048, nk, idg, ob > 0 ? 1u : 0u);
+            }
           }
           tc::mma_commit(ms.bar_mma);
         }
@@ -753,7 +807,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const DevProblem* Pp = args.prob;
   const DevProblem& P = *Pp;
-  const Misc ms = misc_of(smem + args.off_misc);
+  const Misc ms = misc_of(smem + args.off_misc, args.mx_dim, args.mx_taps);
   float* partial = args.partial + (long long)blockIdx.x * P.n_theta;
   const bool want_grad = (args.mode == 0);
   const float* theta = args.theta;
@@ -773,7 +827,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
       cs.ph_ld[b] = 0; cs.ph_free[b] = 0;
     }
     tc::fence_barrier_init();
-    cs.tl_max = args.tl_max; cs.off_P = args.off_P; cs.off_S = args.off_S; cs.off_misc = args.off_misc;
+    cs.tl_max = args.tl_max; cs.off_P = args.off_P; cs.off_S = args.off_S; cs.off_misc = args.off_misc; cs.off_ones = args.off_ones; cs.mx_dim = args.mx_dim; cs.mx_taps = args.mx_taps;
     cs.partial = partial;
     cs.hstash = args.hstash + (long long)blockIdx.x * args.hstash_per_cta;
     cs.zstash = args.zstash + (long long)blockIdx.x * args.zstash_per_cta;
@@ -795,6 +849,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
     }
   }
   if (tid < PINN_MAX_TERMS) ms.tsum[tid] = 0.0;
+  if (tid < 64) {      // ones atom: row r (128 B) holds bf16 1.0 in logical column 0 = 16-byte chunk (0 ^ r)
+    const int r = tid >> 3, ch = tid & 7;
+    *reinterpret_cast<uint4*>(smem + args.off_ones + r * 128 + ch * 16) = make_uint4(ch == r ? 0x00003f80u : 0u, 0u, 0u, 0u);
+  }
   // fp32 blocks of the first / last layers and the tensor-layer biases
   for (int kn = 0; kn < P.n_nets; ++kn) {
     if (args.off_fp[kn] < 0) continue;

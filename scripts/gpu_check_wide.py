@@ -7,7 +7,7 @@ import neuralpde_jl_b200 as npde
 from cases import CASES
 from helpers import engine_eval_sets, load_golden, rel
 
-names = sys.argv[1:] or ["poisson1d_wide", "burgers_wide"]
+names = sys.argv[1:] or ["poisson1d_wide", "burgers_wide", "cfg5_wide"]
 for name in names:
     g, sets, qw = load_golden(name)
     cfg = CASES[name]()

@@ -34,7 +34,7 @@ D = probe(zi, swz_image(X), 0, 0, TB, 1024, 0, 1024, 2048, 2048, 8, idesc(128, 1
 print("  err", err(D, Z.T @ X[:, :16]))
 print("== (W5) column sums with a 1 KB constant B atom: B MN-major, SBO = 0, k-step 0, N = 16: D[o][0] = sum_p Z[p][o]")
 ones = np.zeros((8, 64), dtype=np.float32); ones[:, 0] = 1.0
-for (sbo, step) in ((0, 0), (1024, 0), (0, 2048)):
+for (sbo, step) in ((0, 0), (1024, 0)):
     try:
         D = probe(zi, swz_image(ones), 0, 0, TB, 1024, 0, sbo, 2048, step, 8, idesc(128, 16, 1, 1), 16)
         print("  b_sbo", sbo, "b_step", step, "err col0", err(D[:, 0], Z.sum(axis=0)), "max |cols 1..15|", float(np.abs(D[:, 1:]).max()))

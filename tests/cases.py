@@ -57,6 +57,7 @@ CASES = {
     "cfg5_small": lambda: configs.config5(points=384, bcs_points=64, n_obs=80, width=16, hidden=2),
     "burgers_wide": lambda: configs.config3(points=700, bcs_points=150, width=128, hidden=3),
     "poisson1d_wide": poisson1d_wide_case,
+    "cfg5_wide": lambda: configs.config5(points=500, bcs_points=70, n_obs=90, width=128, hidden=3),
     "mixed": mixed_derivative_case,
     "neumann_sin": neumann_sin_case,
 }

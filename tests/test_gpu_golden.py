@@ -52,7 +52,7 @@ def test_tc_bf16_loss_rtol_1e2(name):
     assert rel(grad, g["grad"]) < 2e-2
 
 
-WIDE_CASES = ["burgers_wide", "poisson1d_wide"]
+WIDE_CASES = ["burgers_wide", "poisson1d_wide", "cfg5_wide"]     # cfg5_wide: 6 channels -> two passes over the network
 
 
 @pytest.mark.parametrize("name", WIDE_CASES)
