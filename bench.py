@@ -317,6 +317,34 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                 alt[m] = {"ms_per_step": ms2, "value": n_pts_global / (ms2 * 1e-3), "loss": float(total_d.item())}
                 r2.engine.close()
             line["config"]["other_modes"] = alt
+            # BASELINE configs[2] (Burgers, 5x128 MLP, 65 536 stochastic points) on the 128-wide tcgen05 path, for context:
+            # a parity-test configuration, not the headline workload
+            try:
+                from neuralpde_jl_b200 import configs as _cfgs
+                c3 = _cfgs.config3()
+                r3 = npde.symbolic_discretize(c3.pde_system, c3.discretization(dtype=dtype, mode="tc_bf16", device=local_rank))
+                th3 = torch.from_numpy(r3.flat_init_params).to(theta_d.device)
+                g3 = torch.empty_like(th3)
+                t3 = torch.empty(r3.engine.n_terms, dtype=th3.dtype, device=th3.device)
+                r3.loss_functions.full_loss_function(r3.flat_init_params)       # draws + uploads the first sample
+                for _ in range(3):
+                    r3.engine.loss_grad_device(th3, g3, t3, total_d, None, stream)
+                e3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+                for a, b in e3:
+                    flush.zero_()
+                    a.record()
+                    r3.engine.loss_grad_device(th3, g3, t3, total_d, None, stream)
+                    b.record()
+                torch.cuda.synchronize()
+                ms3 = float(np.mean([a.elapsed_time(b) for a, b in e3]))
+                fl3 = float(r3.engine.flops_per_eval())
+                line["config"]["other_configs"] = {"cfg3_burgers_5x128_tc_bf16": {
+                    "ms_per_step": ms3, "value": c3.n_pde_points / (ms3 * 1e-3), "unit": UNIT,
+                    "tflops_algorithmic": fl3 / (ms3 * 1e-3) / 1e12, "frac_of_bf16_peak": fl3 / (ms3 * 1e-3) / 1e12 / pk["bf16_tflops"],
+                    "kernel": "tw_loss_grad_kernel", "loss": float(total_d.item())}}
+                r3.engine.close()
+            except Exception as ex:      # context only: never fail the headline line
+                line["config"]["other_configs"] = {"cfg3_burgers_5x128_tc_bf16": {"error": str(ex)[:200]}}
         if world == 1 and not args.no_cpu_baseline:
             sets = rep.point_sets[:n_pde + len(cfg.pde_system.bcs)]
             cores = best_thread_count(cfg, theta_h.astype(np.float64), sets, os.cpu_count() or 1)

@@ -106,7 +106,7 @@ struct pinn_engine {
   long long* tc_dbg = nullptr;   // device buffer for pinn_debug_tc_timeline
   // wide tensor path (128-wide layers): streamed weights, fp32 pre-activation stash
   bool tw = false;
-  int tw_off_P = 0, tw_off_S = 0, tw_off_misc = 0, tw_off_ones = 0, tw_off_fp[PINN_MAX_NETS], tw_wimg[PINN_MAX_NETS];
+  int tw_off_P = 0, tw_off_S = 0, tw_off_misc = 0, tw_off_ones = 0, tw_off_nets = 0, tw_off_fp[PINN_MAX_NETS], tw_wimg[PINN_MAX_NETS];
   int tw_n_images = 0;
   unsigned char tw_img_net[kTwMaxImages], tw_img_layer[kTwMaxImages];
   long long tw_hstash_per_cta = 0, tw_zstash_per_cta = 0;
@@ -564,6 +564,8 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
         ++e->tw_n_images;
       }
     }
+    e->tw_off_nets = (int)o2;
+    o2 += ((size_t)d->n_nets * sizeof(DevNet) + 15) & ~size_t(15);
     e->tw_off_misc = (int)o2;
     o2 += tc_misc_bytes(e->tc_mx_dim, e->tc_mx_taps);
     if (o2 + 1024 > (size_t)max_smem)
@@ -797,7 +799,7 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
     w.wpack = (const uint8_t*)e->tw_wpack; w.tl_max = std::max(e->tc_tl_max, 1);
     w.tile_begin = a.tile_begin; w.tile_end = a.tile_end; w.mode = a.mode; w.resid_out = (float*)a.resid_out;
     w.dbg = e->tc_dbg;
-    w.off_P = e->tw_off_P; w.off_S = e->tw_off_S; w.off_misc = e->tw_off_misc; w.off_ones = e->tw_off_ones; w.mx_dim = e->tc_mx_dim; w.mx_taps = e->tc_mx_taps;
+    w.off_P = e->tw_off_P; w.off_S = e->tw_off_S; w.off_misc = e->tw_off_misc; w.off_ones = e->tw_off_ones; w.off_nets = e->tw_off_nets; w.mx_dim = e->tc_mx_dim; w.mx_taps = e->tc_mx_taps;
     for (int k = 0; k < PINN_MAX_NETS; ++k) {
       w.off_fp[k] = e->tw_off_fp[k]; w.wimg[k] = e->tw_wimg[k];
       int ak = 1;

@@ -88,6 +88,7 @@ struct TwArgs {
   long long* dbg;
   int off_P, off_S, off_misc;       // byte offsets into dynamic shared memory (P: C x 2 tiles, S: 2 x 32 KB)
   int off_ones;                     // 1 KB constant atom (bias gradient by MMA)
+  int off_nets;                     // shared-memory copy of the DevNet descriptors (read every layer)
   int mx_dim, mx_taps;              // sizes of the per-tile coordinate / tap arrays in the misc region
   int off_fp[PINN_MAX_NETS];        // fp32 parameter block per network (-1: unused)
   int net_ak[PINN_MAX_NETS];

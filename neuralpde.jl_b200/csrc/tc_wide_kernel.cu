@@ -30,7 +30,7 @@ constexpr uint32_t TB = kTileBytes;
 
 struct TwShared {
   uint32_t tmem;
-  int tl_max, off_P, off_S, off_misc, off_ones, mx_dim, mx_taps;
+  int tl_max, off_P, off_S, off_misc, off_ones, off_nets, mx_dim, mx_taps;
   float* partial;
   uint8_t* hstash;
   float* zstash;
@@ -147,8 +147,10 @@ __device__ __forceinline__ void tw_fwd_loop(const LoopW lc, const Chan<N1, N2> c
 
 // tensor layer reverse epilogue: stashed pre-activations and output adjoints (TMEM X, or w_last * ubar for the last
 // hidden layer: flag) -> Zbar tiles in P (the bias gradient is a column sum of Zbar_0, taken by an MMA chain against
-// the ones atom).  The stash is read from HBM more often than from L2 (148 CTAs x 1.5 MB in flight > L2), so the loads
-// of two 4-column granules are kept in flight per thread (two register buffers used alternately).
+// the ones atom).  The stash is read from HBM more often than from L2 (148 CTAs x 1.5 MB in flight > L2); the next
+// granule's loads are in flight while the current one is processed.  Measured on the same box (profiles/
+// r01_wide_timeline.md): no prefetch 0.652 ms, this 0.648 ms, two granules ahead 0.737 ms (spills), bf16 stash of the
+// derivative channels 0.669 ms and 4x the gradient error -- the phase is bound by the burst of HBM reads, not by latency.
 template <int N1, int N2, bool PURE, int AK>
 __device__ __forceinline__ void tw_bwd_loop(const LoopW lc, const Chan<N1, N2> ch, const float* ubp, const float2* zst) {
   constexpr int C = 1 + N1 + N2;
@@ -190,16 +192,13 @@ __device__ __forceinline__ void tw_bwd_loop(const LoopW lc, const Chan<N1, N2> c
 #pragma unroll
     for (int c = 0; c < C; ++c) store_half(tile_of(lc.tP, c, ocol), 0u, lc.p, ocol & 63, hb[c], false);
   };
-  load(za, lc.g0);
-  if (lc.g0 + 1 < lc.g1) load(zb, lc.g0 + 1);
+  load(zb, lc.g0);
 #pragma unroll 1
-  for (int g = lc.g0; g < lc.g1; g += 2) {
+  for (int g = lc.g0; g < lc.g1; ++g) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) { za[c][0] = zb[c][0]; za[c][1] = zb[c][1]; }
+    if (g + 1 < lc.g1) load(zb, g + 1);
     process(za, g);
-    if (g + 2 < lc.g1) load(za, g + 2);
-    if (g + 1 < lc.g1) {
-      process(zb, g + 1);
-      if (g + 3 < lc.g1) load(zb, g + 3);
-    }
   }
 }
 
@@ -256,7 +255,7 @@ __device__ __noinline__ uint32_t tw_net_forward(TwShared* cs, const DevProblem* 
   constexpr int C = 1 + N1 + N2;
   const DevTerm& tm = *tmp;
   const int net_id = tm.used_net[slot];
-  const DevNet& net = Pp->nets[net_id];
+  const DevNet& net = reinterpret_cast<const DevNet*>(smem + cs->off_nets)[net_id];
   const DevChan& dc = tm.chan[slot];
   const float* fp = reinterpret_cast<const float*>(smem + cs->off_fp[net_id]);
   uint8_t* tP = smem + cs->off_P;
@@ -415,7 +414,7 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
   constexpr uint32_t DEFER = (C == 4) ? 0x3u : ((C == 3) ? 0x2u : 0x0u);
   const DevTerm& tm = *tmp;
   const int net_id = tm.used_net[slot];
-  const DevNet& net = Pp->nets[net_id];
+  const DevNet& net = reinterpret_cast<const DevNet*>(smem + cs->off_nets)[net_id];
   const DevChan& dc = tm.chan[slot];
   const float* fp = reinterpret_cast<const float*>(smem + cs->off_fp[net_id]);
   uint8_t* tP = smem + cs->off_P;
@@ -827,7 +826,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
       cs.ph_ld[b] = 0; cs.ph_free[b] = 0;
     }
     tc::fence_barrier_init();
-    cs.tl_max = args.tl_max; cs.off_P = args.off_P; cs.off_S = args.off_S; cs.off_misc = args.off_misc; cs.off_ones = args.off_ones; cs.mx_dim = args.mx_dim; cs.mx_taps = args.mx_taps;
+    cs.tl_max = args.tl_max; cs.off_P = args.off_P; cs.off_S = args.off_S; cs.off_misc = args.off_misc; cs.off_ones = args.off_ones; cs.off_nets = args.off_nets; cs.mx_dim = args.mx_dim; cs.mx_taps = args.mx_taps;
     cs.partial = partial;
     cs.hstash = args.hstash + (long long)blockIdx.x * args.hstash_per_cta;
     cs.zstash = args.zstash + (long long)blockIdx.x * args.zstash_per_cta;
@@ -849,6 +848,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
     }
   }
   if (tid < PINN_MAX_TERMS) ms.tsum[tid] = 0.0;
+  {      // network descriptors: every layer of every sweep reads widths / offsets / activations
+    const int nw = P.n_nets * (int)(sizeof(DevNet) / 4);
+    const int* src = reinterpret_cast<const int*>(&P.nets[0]);
+    int* dst = reinterpret_cast<int*>(smem + args.off_nets);
+    for (int i = tid; i < nw; i += kTcThreads) dst[i] = __ldg(src + i);
+  }
   if (tid < 64) {      // ones atom: row r (128 B) holds bf16 1.0 in logical column 0 = 16-byte chunk (0 ^ r)
     const int r = tid >> 3, ch = tid & 7;
     *reinterpret_cast<uint4*>(smem + args.off_ones + r * 128 + ch * 16) = make_uint4(ch == r ? 0x00003f80u : 0u, 0u, 0u, 0u);
