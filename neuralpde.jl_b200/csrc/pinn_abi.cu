@@ -111,6 +111,7 @@ struct pinn_engine {
   unsigned char tw_img_net[kTwMaxImages], tw_img_layer[kTwMaxImages];
   long long tw_hstash_per_cta = 0, tw_zstash_per_cta = 0;
   void* tw_wpack = nullptr;
+  int* tw_counter = nullptr;
   void* tw_zstash = nullptr;
   // workspaces (device)
   void* partial = nullptr;
@@ -618,7 +619,7 @@ int pinn_destroy(pinn_handle e) {
   cudaSetDevice(e->device);
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
   void* ptrs[] = {e->dprob, e->partial, e->term_sums, e->stash, e->gbufs, e->packed,
-                  e->d_theta, e->d_grad, e->d_out, e->adam_m, e->adam_v, e->tw_wpack, e->tw_zstash};
+                  e->d_theta, e->d_grad, e->d_out, e->adam_m, e->adam_v, e->tw_wpack, e->tw_zstash, e->tw_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int t = 0; t < PINN_MAX_TERMS; ++t) {
     if (e->own_pts[t]) cudaFree(e->own_pts[t]);
@@ -673,6 +674,7 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
     if (e->tw) {
       TRY_OR_DESTROY(dev_alloc(&e->tw_zstash, g * (size_t)e->tw_zstash_per_cta * sizeof(float), e));
       TRY_OR_DESTROY(dev_alloc(&e->tw_wpack, (size_t)std::max(e->tw_n_images, 1) * kTwImgBytes, e));
+      TRY_OR_DESTROY(dev_alloc((void**)&e->tw_counter, 64, e));
     }
   }
   TRY_OR_DESTROY(dev_alloc(&e->packed, ((size_t)e->n_theta + PINN_MAX_TERMS) * e->es, e));
@@ -787,6 +789,7 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
     TwPackArgs pk;
     memset(&pk, 0, sizeof pk);
     pk.prob = a.prob; pk.theta = (const float*)a.theta; pk.wpack = (uint8_t*)e->tw_wpack; pk.n_images = e->tw_n_images;
+    pk.tile_counter = e->tw_counter; pk.counter_init = a.tile_begin + grid;
     memcpy(pk.img_net, e->tw_img_net, sizeof pk.img_net);
     memcpy(pk.img_layer, e->tw_img_layer, sizeof pk.img_layer);
     CUDA_TRY(tw_pack_launch(pk, st));
@@ -798,7 +801,7 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
     w.zstash = (float*)e->tw_zstash; w.zstash_per_cta = e->tw_zstash_per_cta;
     w.wpack = (const uint8_t*)e->tw_wpack; w.tl_max = std::max(e->tc_tl_max, 1);
     w.tile_begin = a.tile_begin; w.tile_end = a.tile_end; w.mode = a.mode; w.resid_out = (float*)a.resid_out;
-    w.dbg = e->tc_dbg;
+    w.dbg = e->tc_dbg; w.tile_counter = e->tw_counter;
     w.off_P = e->tw_off_P; w.off_S = e->tw_off_S; w.off_misc = e->tw_off_misc; w.off_ones = e->tw_off_ones; w.off_nets = e->tw_off_nets; w.mx_dim = e->tc_mx_dim; w.mx_taps = e->tc_mx_taps;
     for (int k = 0; k < PINN_MAX_NETS; ++k) {
       w.off_fp[k] = e->tw_off_fp[k]; w.wimg[k] = e->tw_wimg[k];

@@ -89,6 +89,7 @@ struct TwArgs {
   int off_P, off_S, off_misc;       // byte offsets into dynamic shared memory (P: C x 2 tiles, S: 2 x 32 KB)
   int off_ones;                     // 1 KB constant atom (bias gradient by MMA)
   int off_nets;                     // shared-memory copy of the DevNet descriptors (read every layer)
+  int* tile_counter;                // dynamic tile scheduler: next unclaimed tile (reset by tw_pack_kernel)
   int mx_dim, mx_taps;              // sizes of the per-tile coordinate / tap arrays in the misc region
   int off_fp[PINN_MAX_NETS];        // fp32 parameter block per network (-1: unused)
   int net_ak[PINN_MAX_NETS];
@@ -101,6 +102,8 @@ struct TwPackArgs {
   const float* theta;
   uint8_t* wpack;
   int n_images;
+  int* tile_counter;       // reset to counter_init for the fused kernel that follows
+  int counter_init;
   unsigned char img_net[kTwMaxImages], img_layer[kTwMaxImages];
 };
 

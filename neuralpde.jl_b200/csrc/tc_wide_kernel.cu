@@ -39,6 +39,7 @@ struct TwShared {
   long long* dbg;
   int dbg_n;
   int off_fp[PINN_MAX_NETS], wimg[PINN_MAX_NETS];
+  int next_tile;                     // dynamic scheduler: tile claimed for the next iteration
   uint32_t ph_ld[2], ph_free[2];     // phases of the streaming barriers, owned by the issuing lane of warp 0
   uint64_t bar_ld[2], bar_free[2];   // S0 / S1: bytes landed, MMAs that read the buffer retired
 };
@@ -782,6 +783,7 @@ __device__ __noinline__ uint32_t tw_net_backward(TwShared* cs, const DevProblem*
 __global__ void __launch_bounds__(256) tw_pack_kernel(const TwPackArgs a) {
   const int img = blockIdx.x >> 3;
   const int idx = (blockIdx.x & 7) * 256 + threadIdx.x;     // 2048 16-byte chunks per image
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.tile_counter = a.counter_init;
   if (img >= a.n_images) return;
   const DevNet& net = a.prob->nets[a.img_net[img]];
   const int l = a.img_layer[img];
@@ -891,7 +893,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
   dbg_mark(&cs, 2);
   uint32_t phase = 0;
 
-  for (int tile = args.tile_begin + blockIdx.x; tile < args.tile_end; tile += gridDim.x) {
+  // tiles are claimed dynamically after the first one (heavy PDE tiles come first in the enumeration, cheap boundary
+  // tiles last): a static round-robin leaves the CTAs that drew an extra PDE tile 20 % behind the rest
+  for (int tile = args.tile_begin + blockIdx.x; tile < args.tile_end;) {
     int ti = 0;
     while (ti + 1 < P.n_terms && tile >= args.dyn[ti + 1].tile0) ++ti;
     const DevTerm* tmp = &P.terms[ti];
@@ -980,6 +984,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
         PINN_TW_DISPATCH(k1, k2, pu, ak, (phase = tw_net_backward<A1, A2, PU, AK>(&cs, Pp, tmp, slot, phase)));
       }
     }
+    // claim the next tile only now: claiming a tile ahead would hand the last cheap tiles to CTAs that still owe a heavy one
+    if (tid == 0) cs.next_tile = atomicAdd(args.tile_counter, 1);
+    __syncthreads();
+    tile = cs.next_tile;
   }
 
   tc::tc_fence_before();
@@ -1000,8 +1008,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------
 cudaError_t tw_pack_launch(const TwPackArgs& a, cudaStream_t st) {
-  if (a.n_images <= 0) return cudaSuccess;
-  tw_pack_kernel<<<a.n_images * 8, 256, 0, st>>>(a);
+  tw_pack_kernel<<<(a.n_images > 0 ? a.n_images : 1) * 8, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
