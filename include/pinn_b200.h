@@ -208,6 +208,15 @@ int pinn_term_residual(pinn_handle h, int32_t term, const void* dev_theta, void*
                        void* stream);
 int pinn_term_residual_host(pinn_handle h, int32_t term, const void* host_theta, void* host_r);
 
+/* max |dL_term/dtheta_i| and mean |dL_term/dtheta_i| of ONE term's unweighted loss (the other terms enter with
+ * weight 0): what GradientScaleAdaptiveLoss needs per reweighting (reference src/adaptive_losses.jl:115-123 calls
+ * Zygote.gradient(pde_loss_function, theta) per term and takes maximum(abs, .) / mean(abs, .) on the host).
+ * One fused evaluation + one reduction launch; only the two scalars cross to the host.  Synchronises the stream. */
+int pinn_term_grad_stats(pinn_handle h, int32_t term, const void* dev_theta, double* host_max_abs,
+                         double* host_mean_abs, void* stream);
+int pinn_term_grad_stats_host(pinn_handle h, int32_t term, const void* host_theta, double* host_max_abs,
+                              double* host_mean_abs);
+
 /* ---- device-resident optimizer loop ------------------------------------ */
 /* Adam (Optimisers.Adam semantics: m, v, bias-corrected step) fused into the gradient reduction, so a
  * training iteration is two launches with no host round trip.  theta, m, v live in engine-owned device

@@ -177,4 +177,35 @@ cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n
   return cudaGetLastError();
 }
 
+// max |g_i| and sum |g_i| of a gradient vector (one block; the vectors are at most a few MB)
+template <typename real>
+__global__ void __launch_bounds__(1024) grad_stats_kernel(const real* g, long long n, double* out) {
+  __shared__ double smax[32], ssum[32];
+  double mx = 0.0, sm = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 1024) {
+    const double a = fabs((double)g[i]);
+    mx = a > mx ? a : mx;
+    sm += a;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    const double m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+    mx = m2 > mx ? m2 : mx;
+    sm += __shfl_xor_sync(0xffffffffu, sm, o);
+  }
+  if ((threadIdx.x & 31) == 0) { smax[threadIdx.x >> 5] = mx; ssum[threadIdx.x >> 5] = sm; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double m = 0.0, t = 0.0;
+    for (int w = 0; w < 32; ++w) { m = smax[w] > m ? smax[w] : m; t += ssum[w]; }     // fixed order: reproducible
+    out[0] = m;
+    out[1] = n > 0 ? t / (double)n : 0.0;
+  }
+}
+
+cudaError_t grad_stats_launch(int dtype, const void* grad, long long n, double* out2, cudaStream_t st) {
+  if (dtype == PINN_F64) grad_stats_kernel<double><<<1, 1024, 0, st>>>((const double*)grad, n, out2);
+  else grad_stats_kernel<float><<<1, 1024, 0, st>>>((const float*)grad, n, out2);
+  return cudaGetLastError();
+}
+
 }  // namespace pinn

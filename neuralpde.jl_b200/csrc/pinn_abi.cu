@@ -21,6 +21,7 @@ cudaError_t ffma_launch(int dtype, bool bufs_smem, const FfmaArgs& a, int grid, 
 cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
                           int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
                           int want_grad, cudaStream_t st);
+cudaError_t grad_stats_launch(int dtype, const void* grad, long long n, double* out2, cudaStream_t st);
 cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n_terms, const ScaleW& scale_w, void* out_grad,
                           void* out_terms, void* out_total, cudaStream_t st);
 cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
@@ -999,6 +1000,37 @@ int pinn_term_residual_host(pinn_handle e, int32_t term, const void* host_theta,
   }
   cudaFree(dr);
   return rc;
+}
+
+int pinn_term_grad_stats(pinn_handle e, int32_t term, const void* dev_theta, double* host_max_abs, double* host_mean_abs,
+                         void* stream) {
+  if (check_term(e, term, "pinn_term_grad_stats")) return 1;
+  if (!dev_theta || !host_max_abs || !host_mean_abs) return fail("pinn_term_grad_stats: null theta/output");
+  CUDA_TRY(cudaSetDevice(e->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  double w[PINN_MAX_TERMS];
+  for (int t = 0; t < PINN_MAX_TERMS; ++t) w[t] = (t == term) ? 1.0 : 0.0;
+  char* dout = (char*)e->d_out;
+  // gradient of the single unweighted term loss L_term (other terms enter with weight 0)
+  if (pinn_loss_grad(e, dev_theta, w, e->d_grad, dout, dout + (size_t)e->n_terms * e->es, st)) return 1;
+  double* dstats = (double*)e->packed;       // >= 16 bytes, free after pinn_loss_grad returned its results
+  CUDA_TRY(grad_stats_launch(e->dtype, e->d_grad, e->n_theta, dstats, st));
+  e->launches += 1;
+  double hs[2];
+  CUDA_TRY(cudaMemcpyAsync(hs, dstats, sizeof hs, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *host_max_abs = hs[0];
+  *host_mean_abs = hs[1];
+  return 0;
+}
+
+int pinn_term_grad_stats_host(pinn_handle e, int32_t term, const void* host_theta, double* host_max_abs,
+                              double* host_mean_abs) {
+  if (check_term(e, term, "pinn_term_grad_stats_host")) return 1;
+  if (!host_theta) return fail("pinn_term_grad_stats_host: null theta");
+  CUDA_TRY(cudaSetDevice(e->device));
+  CUDA_TRY(cudaMemcpyAsync(e->d_theta, host_theta, (size_t)e->n_theta * e->es, cudaMemcpyHostToDevice, e->own_stream));
+  return pinn_term_grad_stats(e, term, e->d_theta, host_max_abs, host_mean_abs, e->own_stream);
 }
 
 int pinn_comm_unique_id(void* out) {

@@ -36,6 +36,7 @@ EXPORTS = [
     "pinn_term_residual", "pinn_term_residual_host", "pinn_comm_unique_id", "pinn_comm_init",
     "pinn_launch_count", "pinn_set_timing", "pinn_last_kernel_ms", "pinn_workspace_bytes",
     "pinn_flops_per_eval", "pinn_adam_begin", "pinn_adam_iterate", "pinn_adam_theta",
+    "pinn_term_grad_stats", "pinn_term_grad_stats_host",
 ]
 
 
@@ -144,6 +145,10 @@ def load_library():
     lib.pinn_loss_grad.restype = C.c_int
     lib.pinn_loss_grad_host.argtypes = [vp, vp, C.POINTER(dbl), vp, vp, vp]
     lib.pinn_loss_grad_host.restype = C.c_int
+    lib.pinn_term_grad_stats.argtypes = [vp, i32, vp, C.POINTER(dbl), C.POINTER(dbl), vp]
+    lib.pinn_term_grad_stats.restype = C.c_int
+    lib.pinn_term_grad_stats_host.argtypes = [vp, i32, vp, C.POINTER(dbl), C.POINTER(dbl)]
+    lib.pinn_term_grad_stats_host.restype = C.c_int
     lib.pinn_term_residual.argtypes = [vp, i32, vp, vp, vp]
     lib.pinn_term_residual.restype = C.c_int
     lib.pinn_term_residual_host.argtypes = [vp, i32, vp, vp]
@@ -326,6 +331,13 @@ class Engine:
         r = np.empty(int(n), dtype=self.np_dtype)
         _check(self.lib.pinn_term_residual_host(self._h, term, _ptr(th), _ptr(r)))
         return r
+
+    def term_grad_stats_host(self, term: int, theta: np.ndarray):
+        """(max |g|, mean |g|) of the gradient of term `term`'s unweighted loss (GradientScaleAdaptiveLoss)."""
+        th = np.ascontiguousarray(theta, dtype=self.np_dtype)
+        mx, mn = C.c_double(0.0), C.c_double(0.0)
+        _check(self.lib.pinn_term_grad_stats_host(self._h, int(term), _ptr(th), C.byref(mx), C.byref(mn)))
+        return float(mx.value), float(mn.value)
 
     def term_residual_device(self, term: int, dev_theta, dev_r, stream: int = 0):
         _check(self.lib.pinn_term_residual(self._h, term, _ptr(dev_theta), _ptr(dev_r), C.c_void_p(stream)))

@@ -68,3 +68,30 @@ def test_term_weights_and_loss_only():
     _, _, g_b = rep.engine.loss_grad_host(th, np.array([0, 1.0, 1.0, 1.0, 1.0]), True)
     _, _, g_ab = rep.engine.loss_grad_host(th, np.ones(5), True)
     assert rel(g_a + g_b, g_ab) < 1e-12
+
+
+def test_term_grad_stats_and_gradient_scale_adaptive_loss():
+    """pinn_term_grad_stats == max / mean of |gradient of one unweighted term| (reference: Zygote.gradient per term,
+    src/adaptive_losses.jl:107-116); GradientScaleAdaptiveLoss moves the boundary weights by the stated EMA rule."""
+    cfg = configs.config2(n=16, width=16, hidden=2)
+    rep = npde.symbolic_discretize(cfg.pde_system, cfg.discretization(dtype=np.float64))
+    th = rep.flat_init_params
+    n_terms = rep.engine.n_terms
+    stats = []
+    for i in range(n_terms):
+        w = np.zeros(n_terms); w[i] = 1.0
+        _, _, g = rep.engine.loss_grad_host(th, w, True)
+        mx, mn = rep.engine.term_grad_stats_host(i, th)
+        assert abs(mx - np.max(np.abs(g))) <= 1e-13 * mx and abs(mn - np.mean(np.abs(g))) <= 1e-12 * mn
+        stats.append((mx, mn))
+    ada = npde.GradientScaleAdaptiveLoss(2, weight_change_inertia=0.5)
+    disc = cfg.discretization(dtype=np.float64)
+    disc.adaptive_loss = ada
+    rep2 = npde.symbolic_discretize(cfg.pde_system, disc)
+    f = rep2.loss_functions.full_loss_function
+    f(th)                                    # iteration 1: no reweighting
+    f(th)                                    # iteration 2: reweights after the evaluation
+    expected = 0.5 * 1.0 + 0.5 * stats[0][0] / (np.array([s_[1] for s_ in stats[1:]]) + 1e-7)
+    total3 = f(th)                           # evaluated with the new boundary weights
+    terms = rep.engine.loss_grad_host(th, None, False)[1]
+    assert abs(total3 - (terms[0] + float(np.dot(expected, terms[1:])))) <= 1e-10 * abs(total3)

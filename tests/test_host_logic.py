@@ -156,3 +156,16 @@ def test_logging_hooks_noop_and_custom():
     npde.logscalar(lg, 2.0, "loss", 3)
     npde.logvector(lg, [1.0, 2.0], "w", 3)
     assert lg.rows == [("loss", 2.0, 3), ("w/1", 1.0, 3), ("w/2", 2.0, 3)]
+
+
+def test_gradient_scale_adaptive_loss_rule():
+    """bc weights <- a * w + (1 - a) * max|grad pde| / (mean|grad bc_j| + 1e-7), every `reweight_every` iterations
+    (reference src/adaptive_losses.jl:100-126)."""
+    ada = npde.GradientScaleAdaptiveLoss(3, weight_change_inertia=0.9)
+    w = {"pde": np.ones(2), "bc": np.array([1.0, 2.0, 4.0]), "add": np.ones(1)}
+    stats = {0: (5.0, 0.1), 1: (7.0, 0.2), 2: (9.0, 0.5), 3: (1.0, 0.25), 4: (3.0, 2.0)}
+    ada.update(2, [0.0, 0.0], [0.0, 0.0, 0.0], w, term_grad_stats=lambda i: stats[i])
+    np.testing.assert_allclose(w["bc"], [1.0, 2.0, 4.0])                       # not a reweighting iteration
+    ada.update(3, [0.0, 0.0], [0.0, 0.0, 0.0], w, term_grad_stats=lambda i: stats[i])
+    np.testing.assert_allclose(w["bc"], 0.9 * np.array([1.0, 2.0, 4.0]) + 0.1 * 7.0 / (np.array([0.5, 0.25, 2.0]) + 1e-7))
+    np.testing.assert_allclose(w["pde"], [1.0, 1.0])
