@@ -208,6 +208,19 @@ int pinn_term_residual(pinn_handle h, int32_t term, const void* dev_theta, void*
                        void* stream);
 int pinn_term_residual_host(pinn_handle h, int32_t term, const void* host_theta, void* host_r);
 
+/* ---- device-side StochasticTraining sampler -----------------------------------------
+ * The reference draws `lb .+ (ub .- lb) .* rand(T, d, n)` on the host and uploads it on EVERY loss evaluation
+ * (generate_random_points src/training_strategies.jl:242-245, get_loss_function :271-282).  pinn_set_sampler registers
+ * a term's box (one [lb, ub] per point row) and point count and draws the first sample into engine-owned memory;
+ * pinn_resample draws the next sample of every registered term (one small Philox4x32-10 kernel per term, counter =
+ * (point, row group, draw), key = seed + term), so a training iteration has no host round trip.  pinn_adam_iterate
+ * resamples before every step when samplers are registered.  pinn_get_points_host copies a term's current points out
+ * (callbacks, tests).  The random stream necessarily differs from Julia's default RNG; the distribution is the same. */
+int pinn_set_sampler(pinn_handle h, int32_t term, int64_t n, const double* host_lb, const double* host_ub, uint64_t seed,
+                     void* stream);
+int pinn_resample(pinn_handle h, void* stream);
+int pinn_get_points_host(pinn_handle h, int32_t term, void* host_pts);
+
 /* max |dL_term/dtheta_i| and mean |dL_term/dtheta_i| of ONE term's unweighted loss (the other terms enter with
  * weight 0): what GradientScaleAdaptiveLoss needs per reweighting (reference src/adaptive_losses.jl:115-123 calls
  * Zygote.gradient(pde_loss_function, theta) per term and takes maximum(abs, .) / mean(abs, .) on the host).

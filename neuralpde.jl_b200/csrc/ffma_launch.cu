@@ -202,6 +202,64 @@ __global__ void __launch_bounds__(1024) grad_stats_kernel(const real* g, long lo
   }
 }
 
+// ---- device-side StochasticTraining sampler ---------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11): counter = (point index, group of 4 rows, draw), key = seed.  One thread per point
+// writes its `dim` coordinates lb_r + (ub_r - lb_r) * u, u uniform in [0, 1) from the high 24 (float) / 53 (double) bits.
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+struct SampleBox { double lb[PINN_MAX_DIM], ub[PINN_MAX_DIM]; };
+
+template <typename real>
+__global__ void __launch_bounds__(256) sample_uniform_kernel(real* pts, long long n, int dim, SampleBox box,
+                                                              unsigned long long seed, unsigned long long draw) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= n) return;
+  for (int r0 = 0; r0 < dim; r0 += (sizeof(real) == 8 ? 2 : 4)) {
+    uint32_t c[4] = {(uint32_t)p, (uint32_t)(p >> 32), (uint32_t)r0 ^ ((uint32_t)draw << 8), (uint32_t)(draw >> 24)};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    if (sizeof(real) == 8) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int r = r0 + j;
+        if (r < dim) {
+          const unsigned long long bits = ((unsigned long long)c[2 * j] << 32) | c[2 * j + 1];
+          const double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0);
+          pts[p * dim + r] = (real)(box.lb[r] + (box.ub[r] - box.lb[r]) * u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = r0 + j;
+        if (r < dim) {
+          const float u = (float)(c[j] >> 8) * (1.0f / 16777216.0f);
+          pts[p * dim + r] = (real)(box.lb[r] + (box.ub[r] - box.lb[r]) * (double)u);
+        }
+      }
+    }
+  }
+}
+
+cudaError_t sample_uniform_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
+                                  unsigned long long seed, unsigned long long draw, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  SampleBox box;
+  for (int r = 0; r < PINN_MAX_DIM; ++r) { box.lb[r] = r < dim ? lb[r] : 0.0; box.ub[r] = r < dim ? ub[r] : 0.0; }
+  const int blocks = (int)((n + 255) / 256);
+  if (dtype == PINN_F64) sample_uniform_kernel<double><<<blocks, 256, 0, st>>>((double*)pts, n, dim, box, seed, draw);
+  else sample_uniform_kernel<float><<<blocks, 256, 0, st>>>((float*)pts, n, dim, box, seed, draw);
+  return cudaGetLastError();
+}
+
 cudaError_t grad_stats_launch(int dtype, const void* grad, long long n, double* out2, cudaStream_t st) {
   if (dtype == PINN_F64) grad_stats_kernel<double><<<1, 1024, 0, st>>>((const double*)grad, n, out2);
   else grad_stats_kernel<float><<<1, 1024, 0, st>>>((const float*)grad, n, out2);

@@ -22,6 +22,8 @@ cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sum
                           int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
                           int want_grad, cudaStream_t st);
 cudaError_t grad_stats_launch(int dtype, const void* grad, long long n, double* out2, cudaStream_t st);
+cudaError_t sample_uniform_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
+                                  unsigned long long seed, unsigned long long draw, cudaStream_t st);
 cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n_terms, const ScaleW& scale_w, void* out_grad,
                           void* out_terms, void* out_total, cudaStream_t st);
 cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
@@ -139,6 +141,12 @@ struct pinn_engine {
   double adam_lr = 1e-3, adam_b1 = 0.9, adam_b2 = 0.999, adam_eps = 1e-8;
   long long adam_t = 0;
   bool adam_ready = false;
+  // device-side samplers (StochasticTraining): per term box, seed, point count; draw counter shared by all terms
+  bool sampler_on[PINN_MAX_TERMS];
+  double sampler_lb[PINN_MAX_TERMS][PINN_MAX_DIM], sampler_ub[PINN_MAX_TERMS][PINN_MAX_DIM];
+  unsigned long long sampler_seed[PINN_MAX_TERMS];
+  long long sampler_n[PINN_MAX_TERMS];
+  unsigned long long sampler_draw = 0;
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
@@ -652,6 +660,7 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   memset(e->own_pts_cap, 0, sizeof e->own_pts_cap); memset(e->own_qw_cap, 0, sizeof e->own_qw_cap);
   memset(e->dyn, 0, sizeof e->dyn); memset(e->n_global_set, 0, sizeof e->n_global_set);
   memset(e->n_global, 0, sizeof e->n_global);
+  memset(e->sampler_on, 0, sizeof e->sampler_on);
   e->hprob = new DevProblem();
   e->dtype = d->dtype; e->mode = d->mode; e->device = d->device;
   e->es = d->dtype == PINN_F64 ? 8 : 4;
@@ -933,7 +942,10 @@ int pinn_adam_iterate(pinn_handle e, int32_t n_steps, const double* host_weights
   cudaStream_t st = e->own_stream;
   char* dout = (char*)e->d_out;
   const int grid = std::min(e->num_sms, e->total_tiles);
+  bool any_sampler = false;
+  for (int t = 0; t < e->n_terms; ++t) any_sampler = any_sampler || e->sampler_on[t];
   for (int it = 0; it < n_steps; ++it) {
+    if (any_sampler && pinn_resample(e, st)) return 1;      // fresh collocation points every step, drawn on the device
     FfmaArgs a;
     memset(&a, 0, sizeof a);
     fill_args(e, a, e->d_theta, 0);
@@ -1000,6 +1012,56 @@ int pinn_term_residual_host(pinn_handle e, int32_t term, const void* host_theta,
   }
   cudaFree(dr);
   return rc;
+}
+
+static int draw_term(pinn_engine* e, int term, cudaStream_t st) {
+  const int dim = e->hprob->terms[term].dim;
+  const long long n = e->sampler_n[term];
+  if (grow(&e->own_pts[term], &e->own_pts_cap[term], (size_t)n * dim * e->es, e)) return 1;
+  CUDA_TRY(sample_uniform_launch(e->dtype, e->own_pts[term], n, dim, e->sampler_lb[term], e->sampler_ub[term],
+                                 e->sampler_seed[term] + 0x9E3779B97F4A7C15ull * (unsigned long long)(term + 1), e->sampler_draw, st));
+  e->launches += 1;
+  e->dyn[term].pts = e->own_pts[term]; e->dyn[term].qw = nullptr; e->dyn[term].n = n;
+  return 0;
+}
+
+int pinn_set_sampler(pinn_handle e, int32_t term, int64_t n, const double* host_lb, const double* host_ub, uint64_t seed,
+                     void* stream) {
+  if (check_term(e, term, "pinn_set_sampler")) return 1;
+  if (n < 1) return fail("pinn_set_sampler: term %d needs at least one point", term);
+  if (!host_lb || !host_ub) return fail("pinn_set_sampler: null bounds");
+  if (e->reduction[term] == PINN_REDUCE_WSUM)
+    return fail("pinn_set_sampler: term %d is a weighted-sum (quadrature) term; the uniform sampler serves mean(abs2) terms", term);
+  CUDA_TRY(cudaSetDevice(e->device));
+  const int dim = e->hprob->terms[term].dim;
+  for (int r = 0; r < dim; ++r) {
+    if (!(host_lb[r] <= host_ub[r])) return fail("pinn_set_sampler: term %d row %d has lb > ub", term, r);
+    e->sampler_lb[term][r] = host_lb[r]; e->sampler_ub[term][r] = host_ub[r];
+  }
+  e->sampler_on[term] = true; e->sampler_seed[term] = seed; e->sampler_n[term] = n;
+  if (draw_term(e, term, (cudaStream_t)stream)) return 1;
+  retile(e);
+  return 0;
+}
+
+int pinn_resample(pinn_handle e, void* stream) {
+  if (!e) return fail("pinn_resample: null handle");
+  CUDA_TRY(cudaSetDevice(e->device));
+  e->sampler_draw += 1;
+  for (int t = 0; t < e->n_terms; ++t)
+    if (e->sampler_on[t] && draw_term(e, t, (cudaStream_t)stream)) return 1;
+  retile(e);
+  return 0;
+}
+
+int pinn_get_points_host(pinn_handle e, int32_t term, void* host_pts) {
+  if (check_term(e, term, "pinn_get_points_host")) return 1;
+  if (!host_pts) return fail("pinn_get_points_host: null output");
+  CUDA_TRY(cudaSetDevice(e->device));
+  const size_t bytes = (size_t)e->dyn[term].n * e->hprob->terms[term].dim * e->es;
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (bytes) CUDA_TRY(cudaMemcpy(host_pts, e->dyn[term].pts, bytes, cudaMemcpyDeviceToHost));
+  return 0;
 }
 
 int pinn_term_grad_stats(pinn_handle e, int32_t term, const void* dev_theta, double* host_max_abs, double* host_mean_abs,

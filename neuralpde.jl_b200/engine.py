@@ -36,7 +36,7 @@ EXPORTS = [
     "pinn_term_residual", "pinn_term_residual_host", "pinn_comm_unique_id", "pinn_comm_init",
     "pinn_launch_count", "pinn_set_timing", "pinn_last_kernel_ms", "pinn_workspace_bytes",
     "pinn_flops_per_eval", "pinn_adam_begin", "pinn_adam_iterate", "pinn_adam_theta",
-    "pinn_term_grad_stats", "pinn_term_grad_stats_host",
+    "pinn_term_grad_stats", "pinn_term_grad_stats_host", "pinn_set_sampler", "pinn_resample", "pinn_get_points_host",
 ]
 
 
@@ -145,6 +145,12 @@ def load_library():
     lib.pinn_loss_grad.restype = C.c_int
     lib.pinn_loss_grad_host.argtypes = [vp, vp, C.POINTER(dbl), vp, vp, vp]
     lib.pinn_loss_grad_host.restype = C.c_int
+    lib.pinn_set_sampler.argtypes = [vp, i32, i64, C.POINTER(dbl), C.POINTER(dbl), C.c_uint64, vp]
+    lib.pinn_set_sampler.restype = C.c_int
+    lib.pinn_resample.argtypes = [vp, vp]
+    lib.pinn_resample.restype = C.c_int
+    lib.pinn_get_points_host.argtypes = [vp, i32, vp]
+    lib.pinn_get_points_host.restype = C.c_int
     lib.pinn_term_grad_stats.argtypes = [vp, i32, vp, C.POINTER(dbl), C.POINTER(dbl), vp]
     lib.pinn_term_grad_stats.restype = C.c_int
     lib.pinn_term_grad_stats_host.argtypes = [vp, i32, vp, C.POINTER(dbl), C.POINTER(dbl)]
@@ -294,6 +300,29 @@ class Engine:
         flat = buf.ravel(order="F")
         w = None if weights is None else np.ascontiguousarray(weights, dtype=self.np_dtype)
         _check(self.lib.pinn_set_points_host(self._h, term, _ptr(flat), int(pts.shape[1]), _ptr(w), C.c_void_p(stream)))
+
+    def set_sampler(self, term: int, n: int, lb, ub, seed: int = 0, stream: int = 0):
+        """Register a device-side uniform sampler for a term (box lb..ub per point row) and draw the first sample."""
+        lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
+        dim = self.spec.terms[term].dim
+        if lb.shape != (dim,) or ub.shape != (dim,):
+            raise ValueError("term %d expects %d bounds per side, got %s / %s" % (term, dim, lb.shape, ub.shape))
+        _check(self.lib.pinn_set_sampler(self._h, int(term), int(n), lb.ctypes.data_as(C.POINTER(C.c_double)),
+                                         ub.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(int(seed) & (2 ** 64 - 1)),
+                                         C.c_void_p(stream)))
+        self._n_pts = getattr(self, "_n_pts", {})
+        self._n_pts[int(term)] = int(n)
+
+    def resample(self, stream: int = 0):
+        """Draw the next sample of every term that has a device-side sampler."""
+        _check(self.lib.pinn_resample(self._h, C.c_void_p(stream)))
+
+    def get_points_host(self, term: int, n: int) -> np.ndarray:
+        """Current (d, n) point set of a term, copied from the device."""
+        dim = self.spec.terms[term].dim
+        buf = np.empty(int(n) * dim, dtype=self.np_dtype)
+        _check(self.lib.pinn_get_points_host(self._h, int(term), _ptr(buf)))
+        return buf.reshape(int(n), dim).T.copy()
 
     def set_global_count(self, term: int, n_global: int):
         _check(self.lib.pinn_set_global_count(self._h, term, int(n_global)))

@@ -346,8 +346,10 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
 
     # ---- lower equations (src/discretize.jl:505-539) -------------------------------------------------------
     try:
-        pde_terms = [lower_equation(e, vi, param_index, param_values, hoist=True) for e in eqs]
-        bc_terms = [lower_equation(e, vi, param_index, param_values, hoist=True) for e in bcs]
+        # points drawn on the device carry only coordinates: no host-evaluated (hoisted) rows then
+        hoist = not getattr(d.strategy, "device_sampler", False)
+        pde_terms = [lower_equation(e, vi, param_index, param_values, hoist=hoist) for e in eqs]
+        bc_terms = [lower_equation(e, vi, param_index, param_values, hoist=hoist) for e in bcs]
     except LoweringError as ex:
         raise ValueError(str(ex)) from ex
 
@@ -435,10 +437,29 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
         if point_sets[i] is not None:
             upload(i, point_sets[i], quad_w[i])
 
+    device_sampler = isinstance(strategy, StochasticTraining) and strategy.device_sampler
+    if device_sampler:
+        # the reference draws on the host and uploads every call (training_strategies.jl:277-281);
+        # here each term's box is registered once and every draw is one small kernel per term
+        for i, b in enumerate(bounds_all):
+            npts = strategy.points if i < n_pde else strategy.bcs_points
+            lo, hi = shard_range(npts, rank, world)
+            lb = np.array([bb_[0] for bb_ in b], dtype=np.float64)
+            ub = np.array([bb_[1] for bb_ in b], dtype=np.float64)
+            eng.set_sampler(i, hi - lo, lb, ub, strategy.seed + 7919 * rank)
+            if world > 1:
+                eng.set_global_count(i, npts)
+
     def resample():
         """Stochastic: fresh uniform points each call (training_strategies.jl:277-281);
         QuasiRandom(resampling=true): a fresh scrambled sequence each call (:375-380)."""
         if bounds_all is None:
+            return
+        if device_sampler:
+            if state["calls"] > 0:
+                eng.resample()
+            for i in range(len(bounds_all)):
+                point_sets[i] = None            # fetched on demand (rep.current_points)
             return
         if isinstance(strategy, QuasiRandomTraining) and not strategy.resampling and state["calls"] > 0:
             return
@@ -591,13 +612,16 @@ def solve(prob: OptimizationProblem, opt: Adam, maxiters: int = 100, callback: O
     """Minimal stand-in for ``Optimization.solve(prob, Adam(lr); maxiters, callback)``.
 
     Default: a host Adam loop that calls the engine's loss+gradient once per iteration.
-    ``device_loop=True`` (fixed point sets only): theta, m, v stay on the device and the Adam update is
-    fused into the gradient reduction (pinn_adam_iterate); the callback sees the loss every `chunk` steps."""
+    ``device_loop=True`` (fixed point sets, or StochasticTraining with the device-side sampler, which then draws fresh
+    points before every step): theta, m, v stay on the device and the Adam update is fused into the gradient reduction
+    (pinn_adam_iterate); the callback sees the loss every `chunk` steps."""
     rep = prob.representation
     if device_loop:
-        if rep is None or isinstance(rep.strategy, StochasticTraining) or \
-                (isinstance(rep.strategy, QuasiRandomTraining) and rep.strategy.resampling):
-            raise ValueError("device_loop needs fixed point sets (Grid, Quadrature or non-resampled QuasiRandom)")
+        host_resampled = (isinstance(rep.strategy, StochasticTraining) and not rep.strategy.device_sampler) or \
+                         (isinstance(rep.strategy, QuasiRandomTraining) and rep.strategy.resampling) if rep is not None else True
+        if host_resampled:
+            raise ValueError("device_loop needs point sets that live on the device: Grid, Quadrature, non-resampled "
+                             "QuasiRandom, or StochasticTraining(..., device_sampler=True)")
         eng = rep.engine
         eng.adam_begin(prob.u0, opt.lr, opt.beta1, opt.beta2, opt.eps)
         done, obj = 0, float("nan")

@@ -32,6 +32,7 @@ class StochasticTraining(AbstractTrainingStrategy):
     points: int
     bcs_points: Optional[int] = None
     seed: int = 0          # the reference uses the global RNG; a seed makes runs reproducible
+    device_sampler: bool = False   # draw on the GPU (Philox, pinn_set_sampler / pinn_resample) instead of host rand + upload
 
     def __post_init__(self):
         if self.bcs_points is None:

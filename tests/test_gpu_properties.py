@@ -96,3 +96,46 @@ def test_device_loop_rejects_resampled_sets():
     prob = npde.discretize(cfg.pde_system, cfg.discretization(dtype=np.float32))
     with pytest.raises(ValueError, match="fixed point sets"):
         npde.solve(prob, npde.Adam(0.01), maxiters=2, device_loop=True)
+
+
+def test_device_sampler_bounds_determinism_and_oracle_parity():
+    """StochasticTraining with the device-side sampler (pinn_set_sampler / pinn_resample; the reference draws on the host and
+    uploads every call, src/training_strategies.jl:271-282): points stay inside the reference's bounds (get_bounds,
+    src/discretize.jl:299-324), boundary sets keep their constant coordinate, a second engine with the same seed draws the
+    same sequence, each call draws fresh points, and the loss at the drawn points equals the float64 oracle's."""
+    from helpers import oracle_eval
+    from neuralpde_jl_b200.strategies import get_bounds
+    from neuralpde_jl_b200.symbolic import get_vars
+
+    def make():
+        cfg = configs.config3(points=1500, bcs_points=200, width=16, hidden=2)
+        cfg.strategy.device_sampler = True
+        return cfg, npde.symbolic_discretize(cfg.pde_system, cfg.discretization(dtype=np.float64))
+
+    cfg, rep = make()
+    sys_ = cfg.pde_system
+    vi = get_vars(sys_.ivs, sys_.dvs)
+    pb, bb = get_bounds(sys_.domain, sys_.eqs, sys_.bcs, np.float64, vi, cfg.strategy)
+    counts = [1500, 200, 200, 200]
+    th = rep.flat_init_params
+    total = rep.loss_functions.full_loss_function(th)
+    pts = [rep.engine.get_points_host(i, n) for i, n in enumerate(counts)]
+    for p_, b in zip(pts, pb + bb):
+        for r, (lo, hi) in enumerate(b):
+            assert p_[r].min() >= lo and p_[r].max() <= hi
+            if lo == hi:
+                assert np.all(p_[r] == lo)
+            else:       # uniform: mean within 5 sigma, both halves populated
+                assert abs(p_[r].mean() - 0.5 * (lo + hi)) < 5 * (hi - lo) / np.sqrt(12 * p_.shape[1])
+    L, T, G = oracle_eval(cfg, th.astype(np.float64), "exact", pts)
+    assert abs(total - L) <= 1e-10 * abs(L)
+    total2 = rep.loss_functions.full_loss_function(th)          # second call: fresh draw
+    pts2 = rep.engine.get_points_host(0, 1500)
+    assert not np.array_equal(pts2, pts[0]) and total2 != total
+    _, rep_b = make()
+    t_b = rep_b.loss_functions.full_loss_function(th)
+    assert t_b == total and np.array_equal(rep_b.engine.get_points_host(0, 1500), pts[0])
+    # device-resident Adam loop: a fresh sample every step, no host round trip
+    res = npde.solve(npde.discretize(cfg.pde_system, make()[0].discretization(dtype=np.float64)), npde.Adam(1e-3), maxiters=25,
+                     device_loop=True)
+    assert np.isfinite(res.objective) and np.all(np.isfinite(res.u))
