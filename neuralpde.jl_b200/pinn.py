@@ -444,8 +444,7 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
         for i, b in enumerate(bounds_all):
             npts = strategy.points if i < n_pde else strategy.bcs_points
             lo, hi = shard_range(npts, rank, world)
-            lb = np.array([bb_[0] for bb_ in b], dtype=np.float64)
-            ub = np.array([bb_[1] for bb_ in b], dtype=np.float64)
+            lb, ub = (np.asarray(v_, dtype=np.float64) for v_ in b)
             eng.set_sampler(i, hi - lo, lb, ub, strategy.seed + 7919 * rank)
             if world > 1:
                 eng.set_global_count(i, npts)

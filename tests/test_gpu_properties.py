@@ -94,7 +94,7 @@ def test_device_adam_loop_matches_host_adam():
 def test_device_loop_rejects_resampled_sets():
     cfg = configs.config3(points=256, bcs_points=32, width=16, hidden=2)
     prob = npde.discretize(cfg.pde_system, cfg.discretization(dtype=np.float32))
-    with pytest.raises(ValueError, match="fixed point sets"):
+    with pytest.raises(ValueError, match="point sets that live on the device"):
         npde.solve(prob, npde.Adam(0.01), maxiters=2, device_loop=True)
 
 
@@ -121,7 +121,7 @@ def test_device_sampler_bounds_determinism_and_oracle_parity():
     total = rep.loss_functions.full_loss_function(th)
     pts = [rep.engine.get_points_host(i, n) for i, n in enumerate(counts)]
     for p_, b in zip(pts, pb + bb):
-        for r, (lo, hi) in enumerate(b):
+        for r, (lo, hi) in enumerate(zip(*b)):
             assert p_[r].min() >= lo and p_[r].max() <= hi
             if lo == hi:
                 assert np.all(p_[r] == lo)
