@@ -1,6 +1,6 @@
 // tc_kernel.cu -- fused PINN loss+gradient kernel, tcgen05 tensor-core path (sm_100a).
 //
-// One CTA (256 threads) owns a tile of 128 collocation points; a point is a TMEM lane and a
+// One CTA (512 threads) owns a tile of 128 collocation points; a point is a TMEM lane and a
 // row of every operand tile.  The hidden->hidden Dense layers run on the 5th-generation
 // tensor cores (tcgen05.mma, bf16 operands from 128B-swizzled shared-memory tiles, fp32
 // accumulators in TMEM); every derivative channel (value, d/dx_i, d2/dx_i dx_j) is its own
@@ -12,6 +12,8 @@
 //   backward, per tensor layer l:  Z_c   (recompute, 32-column groups)  = H_c * W_l^T
 //                                  Hbar_c[128 x n_in] = Zbar_c[128 x n_out] * W_l     (B MN-major)
 //                                  Wbar_l[n_out x n_in] = sum_c Zbar_c^T * H_c         (A, B MN-major)
+//                                  bbar_l[n_out]        = Zbar_0^T * 1                  (B = constant ones atom)
+//   last layer                  :  wbar_L[n]            = sum_c H_c^T * ubar_c          (B = (hi, lo) pairs of ubar)
 //
 // The first (d -> n) and last (n -> 1) layers are tiny and stay on the CUDA cores inside the
 // same epilogues.  Arithmetic modes: PINN_MODE_TC_BF16 (one MMA per product) and
