@@ -169,3 +169,38 @@ def test_gradient_scale_adaptive_loss_rule():
     ada.update(3, [0.0, 0.0], [0.0, 0.0, 0.0], w, term_grad_stats=lambda i: stats[i])
     np.testing.assert_allclose(w["bc"], 0.9 * np.array([1.0, 2.0, 4.0]) + 0.1 * 7.0 / (np.array([0.5, 0.25, 2.0]) + 1e-7))
     np.testing.assert_allclose(w["pde"], [1.0, 1.0])
+
+
+def _run_ir(prog, rows, taps):
+    """Evaluate a lowered residual program on the host (rows: point-matrix rows incl. hoisted ones)."""
+    val = []
+    for op, a, b, imm in prog:
+        f = {"const": lambda: np.full(rows.shape[1], imm), "coord": lambda: rows[a], "tap": lambda: taps[a],
+             "add": lambda: val[a] + val[b], "sub": lambda: val[a] - val[b], "mul": lambda: val[a] * val[b],
+             "div": lambda: val[a] / val[b], "neg": lambda: -val[a], "powi": lambda: val[a] ** int(imm),
+             "pow": lambda: val[a] ** val[b], "sin": lambda: np.sin(val[a]), "cos": lambda: np.cos(val[a]),
+             "exp": lambda: np.exp(val[a]), "log": lambda: np.log(val[a]), "tanh": lambda: np.tanh(val[a]),
+             "sqrt": lambda: np.sqrt(val[a]), "abs": lambda: np.abs(val[a])}[op]
+        val.append(f())
+    return val[-1]
+
+
+@pytest.mark.parametrize("name", ["cfg2_small", "neumann_sin", "mixed", "cfg3_small"])
+def test_hoisted_and_plain_lowering_agree(name):
+    """Hoisting coordinate-only subexpressions into extra point rows (host-evaluated once per point set) must not change
+    the residual: the device-side sampler path lowers without hoisting, every other path with it."""
+    cfg = CASES[name]()
+    s = cfg.pde_system
+    vi = npde.get_vars(s.ivs, s.dvs)
+    rng = np.random.default_rng(3)
+    for eq in list(s.eqs) + list(s.bcs):
+        plain = npde.lower_equation(eq, vi, hoist=False)
+        hoisted = npde.lower_equation(eq, vi, hoist=True)
+        assert len(plain.taps) == len(hoisted.taps)
+        d = len(vi.indvars) if hasattr(vi, "indvars") else 2
+        X = rng.uniform(0.1, 0.9, size=(plain.augment(np.zeros((d, 1))).shape[0], 9))
+        taps = [rng.standard_normal(9) for _ in plain.taps]
+        r_plain = _run_ir(plain.prog, plain.augment(X), taps)
+        r_hoist = _run_ir(hoisted.prog, hoisted.augment(X), taps)
+        np.testing.assert_allclose(r_hoist, r_plain, rtol=1e-13, atol=1e-14)
+        assert plain.augment(X).shape[0] == X.shape[0]                  # no extra rows without hoisting
