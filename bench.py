@@ -273,6 +273,15 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         flops = eng.flops_per_eval() * (1 if world == 1 else 1)      # per-rank launch
         achieved = flops / (kernel_ms * 1e-3) / 1e12
         value = n_pts_global * args.steps / t_total
+        # DRAM traffic of the dominant kernel: measured once per round with `ncu --set full` (profiles/), not re-measured here
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_traffic.json")) as fh:
+                ent = json.load(fh).get("%s_n%d" % (args.mode, args.n))
+            if ent and world == 1:
+                traffic, traffic_src = int(ent["dram_bytes_read"]) + int(ent["dram_bytes_write"]), ent["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,
@@ -289,7 +298,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                     "ms_per_step": 1e3 * t_e2e / args.steps, "api": "pinn_loss_grad_host"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / pk["bf16_tflops"], "traffic": None, "peak_source": pk_kind,
+                         "frac": achieved / pk["bf16_tflops"], "traffic": traffic, "traffic_unit": "bytes (DRAM read + write per launch, ncu)",
+                         "traffic_source": traffic_src, "peak_source": pk_kind,
                          "kernel": "ffma_loss_grad_kernel" if args.mode == "ffma" else "tc_loss_grad_kernel",
                          "arithmetic": {"ffma": "fp32 FMA on CUDA cores", "tc_bf16": "tcgen05 bf16 x bf16 -> fp32",
                                         "tc_split": "tcgen05 split-bf16 (3 MMAs per product in the forward sweep)"}[args.mode],
