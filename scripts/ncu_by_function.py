@@ -14,7 +14,7 @@ base = data[0][0]
 out = subprocess.run("cuobjdump -elf %s" % sys.argv[2], shell=True, capture_output=True, text=True).stdout
 syms = []
 for line in out.splitlines():
-    m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+0x17\s+(\S+)", line)
+    m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+0x[0-9a-f]+\s+(\S+)", line)
     if m:
         syms.append((int(m.group(1), 16), int(m.group(2), 16), m.group(3)))
 syms.sort()

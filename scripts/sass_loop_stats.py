@@ -4,7 +4,7 @@ obj = sys.argv[1]
 out = subprocess.run("cuobjdump -elf %s" % obj, shell=True, capture_output=True, text=True).stdout
 syms = {}
 for line in out.splitlines():
-    m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+0x17\s+(\S+)", line)
+    m = re.match(r"\s*0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+0x[0-9a-f]+\s+(\S+)", line)
     if m: syms[m.group(3).split('$')[-1]] = (int(m.group(1), 16), int(m.group(2), 16))
 sass = subprocess.run("cuobjdump -sass %s" % obj, shell=True, capture_output=True, text=True).stdout
 ins = []
