@@ -1,6 +1,6 @@
 // tc_probe.cu -- diagnostic: run one chain of tcgen05.mma instructions on caller-supplied
 // shared-memory images and descriptor fields and return the fp32 accumulator.  Used by
-// tests/test_gpu_tc_probe.py to pin the descriptor conventions (K-major / MN-major, LBO /
+// scripts/tc_probe.py and scripts/tc_probe_wide.py to pin the descriptor conventions (K-major / MN-major, LBO /
 // SBO meaning, k-step advance) against numpy before the fused kernel relies on them.
 #include <cuda_runtime.h>
 #include <stdint.h>
