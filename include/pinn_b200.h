@@ -236,10 +236,15 @@ int pinn_term_grad_stats_host(pinn_handle h, int32_t term, const void* host_thet
                               double* host_mean_abs);
 
 /* ---- device-resident optimizer loop ------------------------------------ */
-/* Adam (Optimisers.Adam semantics: m, v, bias-corrected step) fused into the gradient reduction, so a
- * training iteration is two launches with no host round trip.  theta, m, v live in engine-owned device
- * memory.  Valid while the point sets stay fixed (Grid / fixed-node quadrature / non-resampled sets);
- * the reference's per-iteration host loop (Optimization.solve + Zygote) is what this replaces. */
+/* Adam (Optimisers.Adam semantics: m, v, bias-corrected step) applied in the TAIL of the fused kernel, right after
+ * the in-kernel gradient reduction (and, at nranks > 1, the peer-memory sum): a training iteration is ONE launch
+ * (+ one sampler launch per sampled term, + the weight-pack launch on the 128-wide path) with no host round trip.
+ * theta, m, v, the step counter and the sampler draw counter live in engine-owned device memory, so
+ * pinn_adam_iterate captures its n_steps iterations once into a CUDA graph and replays it while the arguments
+ * stay the same (PINN_B200_NO_GRAPH=1 disables the capture).  Point sets: fixed (Grid / fixed-node quadrature /
+ * non-resampled) or drawn by the device-side samplers.  Multi-GPU: every rank applies the identical update to its
+ * replica (needs the peer-memory path, see pinn_comm_info).  The reference's per-iteration host loop
+ * (Optimization.solve + Zygote + Optimisers.Adam) is what this replaces. */
 int pinn_adam_begin(pinn_handle h, const void* host_theta0, double lr, double beta1, double beta2, double eps);
 /* run n_steps iterations; host_total (nullable) receives the loss of the LAST evaluated theta,
  * host_term_losses (nullable) its per-term losses.  Synchronises at the end. */
@@ -252,6 +257,15 @@ int pinn_adam_theta(pinn_handle h, void* host_theta_out);
  * distributed (rank 0 obtains it from pinn_comm_unique_id). */
 int pinn_comm_unique_id(void* out_128_bytes);
 int pinn_comm_init(pinn_handle h, const void* unique_id_128_bytes, int32_t rank, int32_t nranks);
+/* pinn_comm_init also maps every rank's symmetric gradient buffer into this process (CUDA IPC over NVLink peer
+ * access, handles exchanged through the communicator).  When that succeeds on all ranks the sum over ranks runs INSIDE
+ * the fused kernel: each CTA publishes its slice of the reduced gradient, signals per-slice flags in the peers'
+ * memory and adds the peers' slices in rank order -- no ncclAllReduce, no extra launch, identical bits on every
+ * rank.  Otherwise (GPUs without peer access, ranks that are threads of one process, PINN_B200_NO_P2P=1) the step is
+ * fused kernel -> ncclAllReduce -> unpack.  pinn_comm_info reports which: *fused_p2p = 1 / 0, and returns the reason
+ * for a fallback ("" when none).  All ranks must issue the same sequence of pinn_loss_grad / pinn_adam_iterate calls
+ * (SPMD), and synchronise with each other before destroying their handles. */
+const char* pinn_comm_info(pinn_handle h, int32_t* fused_p2p);
 
 /* ---- introspection ------------------------------------------------------------------ */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */

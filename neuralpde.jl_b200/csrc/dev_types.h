@@ -70,11 +70,48 @@ struct DevProblem {
   DevTerm terms[PINN_MAX_TERMS];
 };
 
+// per term scale (L_k = scale_k * sum_p qw_p r_p^2) and loss weight, passed by value
+struct ScaleW {
+  double scale[PINN_MAX_TERMS];
+  double w[PINN_MAX_TERMS];
+};
+
+// ---- fused kernel tail (tail.cuh): grid barrier, slice reduction, one-shot peer allreduce, optimizer step ----------
+constexpr int kMaxRanks = 8;       // GPUs of one NVSwitch domain that share the peer-memory allreduce
+constexpr int kTailSlots = 256;    // per-slice flags per peer (>= CTAs per launch)
+
+struct TailState {                 // device-resident, owned by the handle (zero-initialised)
+  unsigned int count, gen;         // self-resetting generation barrier over the CTAs of one launch
+  unsigned int step;               // launches with a tail so far (flag value / buffer parity of the peer allreduce)
+  unsigned int pad;
+  unsigned long long adam_t;       // optimizer steps taken (bias correction)
+  unsigned long long draw;         // sampler draw counter (advanced by the tail so captured graphs resample)
+};
+
+struct TailArgs {
+  TailState* state;                // null: no tail (the launch only writes per-CTA partials)
+  void* out_grad;                  // [n_theta] or null
+  void* out_terms;                 // [n_terms] unweighted term losses
+  void* out_total;                 // weighted total or null
+  void* adam_theta;                // non-null: Adam step applied in place (theta, m, v)
+  void* adam_m;
+  void* adam_v;
+  double adam_lr, adam_b1, adam_b2, adam_eps;
+  unsigned long long timeout_ns;   // spin bound of the barriers (a lost peer traps instead of hanging)
+  int bump_draw;                   // advance state->draw (device-side samplers present)
+  int nranks, rank;
+  long long terms_off;             // byte offset of the double[PINN_MAX_TERMS] term-loss block inside a peer buffer
+  void* peer_buf[2][kMaxRanks];    // symmetric [grad | term losses] buffers, by step parity, of every rank (peer-mapped)
+  unsigned int* peer_flags[kMaxRanks];   // [kMaxRanks][kTailSlots] flags of every rank (peer-mapped)
+  ScaleW sw;
+};
+
 // kernel launch arguments (passed by value, < 4 KB)
 struct FfmaArgs {
   const DevProblem* prob;
   const void* theta;
-  void* partial;          // [grid][n_theta] per-CTA gradient partials (scalar type)
+  void* partial;          // [grid][partial_stride] per-CTA gradient partials (scalar type)
+  long long partial_stride;   // n_theta rounded up to 4 scalars (16-byte aligned rows for the vector loads of the tail)
   double* term_sums;      // [grid][PINN_MAX_TERMS] per-CTA sum_p qw_p r_p^2
   void* stash;            // [grid][stash_per_cta]
   void* gbufs;            // [grid][2*buf_elems] global fallback for the two activation buffers
@@ -90,12 +127,7 @@ struct FfmaArgs {
   void* resid_out;        // mode 2: r[n] of the selected term
   double seed[PINN_MAX_TERMS];  // w_k * scale_k : d(total)/d(sum_p qw r^2) of each term
   TermDyn dyn[PINN_MAX_TERMS];
-};
-
-// per-term scale (L_k = scale_k * sum_p qw_p r_p^2) and loss weight, passed by value
-struct ScaleW {
-  double scale[PINN_MAX_TERMS];
-  double w[PINN_MAX_TERMS];
+  TailArgs tail;
 };
 
 }  // namespace pinn

@@ -18,8 +18,7 @@ cudaError_t PINN_LAUNCH_NAME(const FfmaArgs& a, int grid, size_t smem, cudaStrea
   auto k = ffma_loss_grad_kernel<PINN_INST_REAL, (PINN_INST_BUFS != 0)>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  k<<<grid, kThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_fused_kernel(k, a, grid, kThreads, smem, st, a.tail.state != nullptr);
 }
 
 }  // namespace pinn

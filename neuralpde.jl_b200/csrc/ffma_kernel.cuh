@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include "dev_types.h"
+#include "tail.cuh"
 
 namespace pinn {
 
@@ -517,7 +518,7 @@ __global__ void __launch_bounds__(kThreads, 1) ffma_loss_grad_kernel(const FfmaA
   real* qws = sm; sm += kTilePts;       // quadrature weight per point (0 for padded lanes)
   double* tsum = reinterpret_cast<double*>(sm);  // [PINN_MAX_TERMS], 8-byte aligned by construction
 
-  real* partial = reinterpret_cast<real*>(args.partial) + (long long)blockIdx.x * P.n_theta;
+  real* partial = reinterpret_cast<real*>(args.partial) + (long long)blockIdx.x * args.partial_stride;
   real* stash = reinterpret_cast<real*>(args.stash) + (long long)blockIdx.x * args.stash_per_cta;
   const bool want_grad = (args.mode == 0);
 
@@ -701,6 +702,10 @@ __global__ void __launch_bounds__(kThreads, 1) ffma_loss_grad_kernel(const FfmaA
 
   __syncthreads();
   if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = tsum[tid];
+  // gradient reduction, optimizer step and the multi-GPU sum in the kernel tail (tail.cuh)
+  if (args.tail.state)
+    fused_tail<real, kThreads>(args.tail, reinterpret_cast<const real*>(args.partial), args.partial_stride, args.term_sums,
+                               P.n_theta, P.n_terms, want_grad ? 1 : 0, taps);
 }
 
 

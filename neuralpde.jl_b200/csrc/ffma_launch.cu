@@ -13,7 +13,7 @@ namespace pinn {
 // When `packed` is non-null (multi-GPU), grad and the term losses are written contiguously
 // into packed[0..n_theta+n_terms) for a single allreduce and finish_kernel unpacks.
 template <typename real>
-__global__ void reduce_kernel(const real* __restrict__ partial, const double* __restrict__ term_sums, int nb,
+__global__ void reduce_kernel(const real* __restrict__ partial, long long stride, const double* __restrict__ term_sums, int nb,
                               long long n_theta, int n_terms, const ScaleW sw,
                               real* out_grad, real* out_terms, real* out_total, int want_grad) {
   // block = 32 gradient entries x 8 slices of the CTA partials; fixed summation order (slice-major)
@@ -25,7 +25,7 @@ __global__ void reduce_kernel(const real* __restrict__ partial, const double* __
     if (i < n_theta) {
       const int chunk = (nb + 7) / 8;
       const int b0 = ty * chunk, b1 = (b0 + chunk < nb) ? b0 + chunk : nb;
-      for (int b = b0; b < b1; ++b) s += partial[(long long)b * n_theta + i];
+      for (int b = b0; b < b1; ++b) s += partial[(long long)b * stride + i];
     }
     red[ty][tx] = s;
     __syncthreads();
@@ -53,7 +53,7 @@ __global__ void reduce_kernel(const real* __restrict__ partial, const double* __
 
 // gradient reduction fused with the Adam update: theta, m, v updated in place (single-GPU path)
 template <typename real>
-__global__ void reduce_adam_kernel(const real* __restrict__ partial, const double* __restrict__ term_sums, int nb,
+__global__ void reduce_adam_kernel(const real* __restrict__ partial, long long stride, const double* __restrict__ term_sums, int nb,
                                    long long n_theta, int n_terms, const ScaleW sw, real* theta, real* m, real* v,
                                    double lr_t, double beta1, double beta2, double eps_t, real* out_terms, real* out_total) {
   __shared__ real red[8][33];
@@ -63,7 +63,7 @@ __global__ void reduce_adam_kernel(const real* __restrict__ partial, const doubl
   if (i < n_theta) {
     const int chunk = (nb + 7) / 8;
     const int b0 = ty * chunk, b1 = (b0 + chunk < nb) ? b0 + chunk : nb;
-    for (int b = b0; b < b1; ++b) s += partial[(long long)b * n_theta + i];
+    for (int b = b0; b < b1; ++b) s += partial[(long long)b * stride + i];
   }
   red[ty][tx] = s;
   __syncthreads();
@@ -133,32 +133,32 @@ cudaError_t ffma_launch(int dtype, bool bufs_smem, const FfmaArgs& a, int grid, 
   return bufs_smem ? ffma_launch_float_smem(a, grid, smem, st) : ffma_launch_float_gmem(a, grid, smem, st);
 }
 
-cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+cudaError_t reduce_launch(int dtype, const void* partial, long long stride, const double* term_sums, int nb, long long n_theta,
                           int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
                           int want_grad, cudaStream_t st) {
   long long n = want_grad ? n_theta : 1;
   int blocks = (int)((n + 31) / 32);
   if (blocks < 1) blocks = 1;
   if (dtype == PINN_F64)
-    reduce_kernel<double><<<blocks, 256, 0, st>>>((const double*)partial, term_sums, nb, n_theta, n_terms, scale_w,
+    reduce_kernel<double><<<blocks, 256, 0, st>>>((const double*)partial, stride, term_sums, nb, n_theta, n_terms, scale_w,
                                                    (double*)out_grad, (double*)out_terms, (double*)out_total,
                                                    want_grad);
   else
-    reduce_kernel<float><<<blocks, 256, 0, st>>>((const float*)partial, term_sums, nb, n_theta, n_terms, scale_w,
+    reduce_kernel<float><<<blocks, 256, 0, st>>>((const float*)partial, stride, term_sums, nb, n_theta, n_terms, scale_w,
                                                   (float*)out_grad, (float*)out_terms, (float*)out_total, want_grad);
   return cudaGetLastError();
 }
 
-cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+cudaError_t reduce_adam_launch(int dtype, const void* partial, long long stride, const double* term_sums, int nb, long long n_theta,
                                int n_terms, const ScaleW& sw, void* theta, void* m, void* v, double lr_t, double beta1,
                                double beta2, double eps_t, void* out_terms, void* out_total, cudaStream_t st) {
   int blocks = (int)((n_theta + 31) / 32);
   if (dtype == PINN_F64)
-    reduce_adam_kernel<double><<<blocks, 256, 0, st>>>((const double*)partial, term_sums, nb, n_theta, n_terms, sw,
+    reduce_adam_kernel<double><<<blocks, 256, 0, st>>>((const double*)partial, stride, term_sums, nb, n_theta, n_terms, sw,
                                                         (double*)theta, (double*)m, (double*)v, lr_t, beta1, beta2, eps_t,
                                                         (double*)out_terms, (double*)out_total);
   else
-    reduce_adam_kernel<float><<<blocks, 256, 0, st>>>((const float*)partial, term_sums, nb, n_theta, n_terms, sw,
+    reduce_adam_kernel<float><<<blocks, 256, 0, st>>>((const float*)partial, stride, term_sums, nb, n_theta, n_terms, sw,
                                                        (float*)theta, (float*)m, (float*)v, lr_t, beta1, beta2, eps_t,
                                                        (float*)out_terms, (float*)out_total);
   return cudaGetLastError();
@@ -220,9 +220,11 @@ struct SampleBox { double lb[PINN_MAX_DIM], ub[PINN_MAX_DIM]; };
 
 template <typename real>
 __global__ void __launch_bounds__(256) sample_uniform_kernel(real* pts, long long n, int dim, SampleBox box,
-                                                              unsigned long long seed, unsigned long long draw) {
+                                                              unsigned long long seed, unsigned long long draw,
+                                                              const unsigned long long* draw_dev) {
   const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
   if (p >= n) return;
+  if (draw_dev) draw += *draw_dev;       // device-side counter advanced by the fused kernel's tail (graph replays)
   for (int r0 = 0; r0 < dim; r0 += (sizeof(real) == 8 ? 2 : 4)) {
     uint32_t c[4] = {(uint32_t)p, (uint32_t)(p >> 32), (uint32_t)r0 ^ ((uint32_t)draw << 8), (uint32_t)(draw >> 24)};
     philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
@@ -250,13 +252,14 @@ __global__ void __launch_bounds__(256) sample_uniform_kernel(real* pts, long lon
 }
 
 cudaError_t sample_uniform_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
-                                  unsigned long long seed, unsigned long long draw, cudaStream_t st) {
+                                  unsigned long long seed, unsigned long long draw, const unsigned long long* draw_dev,
+                                  cudaStream_t st) {
   if (n <= 0) return cudaSuccess;
   SampleBox box;
   for (int r = 0; r < PINN_MAX_DIM; ++r) { box.lb[r] = r < dim ? lb[r] : 0.0; box.ub[r] = r < dim ? ub[r] : 0.0; }
   const int blocks = (int)((n + 255) / 256);
-  if (dtype == PINN_F64) sample_uniform_kernel<double><<<blocks, 256, 0, st>>>((double*)pts, n, dim, box, seed, draw);
-  else sample_uniform_kernel<float><<<blocks, 256, 0, st>>>((float*)pts, n, dim, box, seed, draw);
+  if (dtype == PINN_F64) sample_uniform_kernel<double><<<blocks, 256, 0, st>>>((double*)pts, n, dim, box, seed, draw, draw_dev);
+  else sample_uniform_kernel<float><<<blocks, 256, 0, st>>>((float*)pts, n, dim, box, seed, draw, draw_dev);
   return cudaGetLastError();
 }
 

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -18,15 +19,16 @@
 namespace pinn {
 size_t ffma_smem_bytes(int dtype, long long buf_elems, int w_area, bool bufs_smem);
 cudaError_t ffma_launch(int dtype, bool bufs_smem, const FfmaArgs& a, int grid, size_t smem, cudaStream_t st);
-cudaError_t reduce_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+cudaError_t reduce_launch(int dtype, const void* partial, long long stride, const double* term_sums, int nb, long long n_theta,
                           int n_terms, const ScaleW& scale_w, void* out_grad, void* out_terms, void* out_total,
                           int want_grad, cudaStream_t st);
 cudaError_t grad_stats_launch(int dtype, const void* grad, long long n, double* out2, cudaStream_t st);
 cudaError_t sample_uniform_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
-                                  unsigned long long seed, unsigned long long draw, cudaStream_t st);
+                                  unsigned long long seed, unsigned long long draw, const unsigned long long* draw_dev,
+                                  cudaStream_t st);
 cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n_terms, const ScaleW& scale_w, void* out_grad,
                           void* out_terms, void* out_total, cudaStream_t st);
-cudaError_t reduce_adam_launch(int dtype, const void* partial, const double* term_sums, int nb, long long n_theta,
+cudaError_t reduce_adam_launch(int dtype, const void* partial, long long stride, const double* term_sums, int nb, long long n_theta,
                                int n_terms, const ScaleW& sw, void* theta, void* m, void* v, double lr_t, double beta1,
                                double beta2, double eps_t, void* out_terms, void* out_total, cudaStream_t st);
 }  // namespace pinn
@@ -37,13 +39,14 @@ using namespace pinn;
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat32 = 7, ncclFloat64 = 8, ncclSumOp = 0 };
+enum { ncclInt8 = 0, ncclInt32 = 2, ncclFloat32 = 7, ncclFloat64 = 8, ncclSumOp = 0, ncclMinOp = 3 };
 struct NcclApi {
   void* lib = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi g_nccl;
@@ -76,6 +79,7 @@ static bool load_nccl() {
   g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(g_nccl.lib, "ncclGetErrorString");
   return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce;
 }
@@ -86,7 +90,7 @@ struct pinn_engine {
   DevProblem* hprob = nullptr;   // host copy (heap: ~250 KB)
   DevProblem* dprob = nullptr;   // device copy
   int n_terms = 0;
-  long long n_theta = 0;
+  long long n_theta = 0, partial_stride = 0;
   double term_scale[PINN_MAX_TERMS];     // WSUM scale (MEAN: 1/n_global at launch time)
   int reduction[PINN_MAX_TERMS];
   long long n_global[PINN_MAX_TERMS];
@@ -147,9 +151,24 @@ struct pinn_engine {
   unsigned long long sampler_seed[PINN_MAX_TERMS];
   long long sampler_n[PINN_MAX_TERMS];
   unsigned long long sampler_draw = 0;
+  // fused kernel tail (tail.cuh): device-resident barrier / step state; PINN_B200_TAIL=0 selects the separate reduce kernel
+  TailState* d_state = nullptr;
+  bool tail_on = true;
+  unsigned long long tail_timeout_ns = 20ull * 1000000000ull;
+  // captured iteration graph of the device-resident Adam loop
+  cudaGraphExec_t adam_graph = nullptr;
+  int adam_graph_n = 0;
+  unsigned long long adam_graph_key = 0;
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
+  // peer-memory allreduce (NVLink): symmetric region = [buf parity 0 | buf parity 1 | flags], mapped from every rank
+  bool p2p = false;
+  void* sym = nullptr;
+  size_t sym_buf_bytes = 0;
+  long long sym_terms_off = 0;
+  void* peer_base[kMaxRanks];
+  char p2p_why[160];
   // introspection
   long long launches = 0;
   bool timing = false;
@@ -626,8 +645,16 @@ int pinn_abi_version(void) { return PINN_ABI_VERSION; }
 int pinn_destroy(pinn_handle e) {
   if (!e) return 0;
   cudaSetDevice(e->device);
+  if (e->adam_graph) cudaGraphExecDestroy(e->adam_graph);
+  if (e->p2p) {
+    // peers may still be reading this rank's symmetric buffers inside their last step: callers synchronise the ranks
+    // (any collective / barrier) before destroying handles; here only this device is drained
+    cudaDeviceSynchronize();
+    for (int r = 0; r < e->nranks; ++r)
+      if (r != e->rank && e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
+  }
   if (e->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(e->comm);
-  void* ptrs[] = {e->dprob, e->partial, e->term_sums, e->stash, e->gbufs, e->packed,
+  void* ptrs[] = {e->dprob, e->partial, e->term_sums, e->stash, e->gbufs, e->packed, e->d_state, e->sym,
                   e->d_theta, e->d_grad, e->d_out, e->adam_m, e->adam_v, e->tw_wpack, e->tw_zstash, e->tw_counter};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (int t = 0; t < PINN_MAX_TERMS; ++t) {
@@ -661,6 +688,8 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   memset(e->dyn, 0, sizeof e->dyn); memset(e->n_global_set, 0, sizeof e->n_global_set);
   memset(e->n_global, 0, sizeof e->n_global);
   memset(e->sampler_on, 0, sizeof e->sampler_on);
+  memset(e->peer_base, 0, sizeof e->peer_base);
+  e->p2p_why[0] = 0;
   e->hprob = new DevProblem();
   e->dtype = d->dtype; e->mode = d->mode; e->device = d->device;
   e->es = d->dtype == PINN_F64 ? 8 : 4;
@@ -674,7 +703,8 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   cudaError_t err = cudaMemcpy(e->dprob, e->hprob, sizeof(DevProblem), cudaMemcpyHostToDevice);
   if (err != cudaSuccess) { fail("pinn_create: upload failed: %s", cudaGetErrorString(err)); pinn_destroy(e); return 1; }
   const size_t g = (size_t)e->num_sms;
-  TRY_OR_DESTROY(dev_alloc(&e->partial, g * (size_t)e->n_theta * e->es, e));
+  e->partial_stride = (e->n_theta + 3) & ~3LL;
+  TRY_OR_DESTROY(dev_alloc(&e->partial, g * (size_t)e->partial_stride * e->es, e));
   TRY_OR_DESTROY(dev_alloc((void**)&e->term_sums, g * PINN_MAX_TERMS * sizeof(double), e));
   if (e->mode == PINN_MODE_FFMA) {
     TRY_OR_DESTROY(dev_alloc(&e->stash, g * (size_t)e->stash_per_cta * e->es, e));
@@ -688,12 +718,23 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
     }
   }
   TRY_OR_DESTROY(dev_alloc(&e->packed, ((size_t)e->n_theta + PINN_MAX_TERMS) * e->es, e));
+  TRY_OR_DESTROY(dev_alloc((void**)&e->d_state, sizeof(TailState), e));
+  err = cudaMemset(e->d_state, 0, sizeof(TailState));
+  if (err != cudaSuccess) { fail("pinn_create: state init failed: %s", cudaGetErrorString(err)); pinn_destroy(e); return 1; }
+  {
+    const char* tv = getenv("PINN_B200_TAIL");
+    e->tail_on = !(tv && tv[0] == '0');
+    const char* to = getenv("PINN_B200_TAIL_TIMEOUT_S");
+    if (to && atof(to) > 0) e->tail_timeout_ns = (unsigned long long)(atof(to) * 1e9);
+  }
   TRY_OR_DESTROY(dev_alloc(&e->d_theta, (size_t)e->n_theta * e->es, e));
   TRY_OR_DESTROY(dev_alloc(&e->d_grad, (size_t)e->n_theta * e->es, e));
   TRY_OR_DESTROY(dev_alloc(&e->d_out, (PINN_MAX_TERMS + 1) * e->es, e));
   err = cudaMallocHost(&e->h_pin_in, (size_t)e->n_theta * e->es);
   if (err == cudaSuccess) err = cudaMallocHost(&e->h_pin_out, ((size_t)e->n_theta + PINN_MAX_TERMS + 1) * e->es);
-  if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking);
+  // a BLOCKING stream: the *_host entry points run here and must order after uploads / sampler draws that callers
+  // enqueue on the legacy default stream (pinn_set_points_host, pinn_set_sampler, pinn_resample with stream = 0)
+  if (err == cudaSuccess) err = cudaStreamCreate(&e->own_stream);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev0);
   if (err == cudaSuccess) err = cudaEventCreate(&e->ev1);
   if (err != cudaSuccess) { fail("pinn_create: host staging setup failed: %s", cudaGetErrorString(err)); pinn_destroy(e); return 1; }
@@ -782,14 +823,15 @@ static int prepare_scales(pinn_engine* e, const double* host_weights, FfmaArgs& 
 }
 
 static void fill_args(pinn_engine* e, FfmaArgs& a, const void* theta, int mode) {
-  a.prob = e->dprob; a.theta = theta; a.partial = e->partial; a.term_sums = e->term_sums; a.stash = e->stash;
+  a.prob = e->dprob; a.theta = theta; a.partial = e->partial; a.partial_stride = e->partial_stride; a.term_sums = e->term_sums; a.stash = e->stash;
   a.gbufs = e->gbufs; a.stash_per_cta = e->stash_per_cta; a.buf_elems = e->buf_elems; a.ldc = e->ldc;
   a.w_area = e->w_area; a.weights_resident = e->weights_resident; a.n_tiles = e->total_tiles;
   a.tile_begin = 0; a.tile_end = e->total_tiles; a.mode = mode; a.resid_out = nullptr;
   for (int t = 0; t < PINN_MAX_TERMS; ++t) a.dyn[t] = e->dyn[t];
 }
 
-// launch the fused kernel of the handle's mode over tiles [tile_begin, tile_end)
+// launch the fused kernel of the handle's mode over tiles [tile_begin, tile_end); a.tail.state != null attaches the
+// in-kernel tail (gradient reduction / optimizer / peer allreduce) and makes the launch cooperative
 static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_t st) {
   if (e->mode == PINN_MODE_FFMA) {
     CUDA_TRY(ffma_launch(e->dtype, e->bufs_smem, a, grid, e->smem, st));
@@ -806,7 +848,7 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
     e->launches += 1;
     TwArgs w;
     memset(&w, 0, sizeof w);
-    w.prob = a.prob; w.theta = (const float*)a.theta; w.partial = (float*)a.partial; w.term_sums = a.term_sums;
+    w.prob = a.prob; w.theta = (const float*)a.theta; w.partial = (float*)a.partial; w.partial_stride = a.partial_stride; w.term_sums = a.term_sums;
     w.hstash = (uint8_t*)e->stash; w.hstash_per_cta = e->tw_hstash_per_cta;
     w.zstash = (float*)e->tw_zstash; w.zstash_per_cta = e->tw_zstash_per_cta;
     w.wpack = (const uint8_t*)e->tw_wpack; w.tl_max = std::max(e->tc_tl_max, 1);
@@ -823,12 +865,13 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
       w.net_ak[k] = ak;
     }
     for (int k = 0; k < PINN_MAX_TERMS; ++k) { w.seed[k] = a.seed[k]; w.dyn[k] = a.dyn[k]; }
+    w.tail = a.tail;
     CUDA_TRY(tw_launch(w, grid, e->smem, st));
     return 0;
   }
   TcArgs t;
   memset(&t, 0, sizeof t);
-  t.prob = a.prob; t.theta = (const float*)a.theta; t.partial = (float*)a.partial; t.term_sums = a.term_sums;
+  t.prob = a.prob; t.theta = (const float*)a.theta; t.partial = (float*)a.partial; t.partial_stride = a.partial_stride; t.term_sums = a.term_sums;
   t.stash = (uint8_t*)e->stash; t.stash_per_cta = e->tc_stash_per_cta; t.split = e->tc_split; t.tl_max = std::max(e->tc_tl_max, 1);
   t.tile_begin = a.tile_begin; t.tile_end = a.tile_end; t.mode = a.mode; t.resid_out = (float*)a.resid_out;
   t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc; t.off_ones = e->tc_off_ones; t.mx_dim = e->tc_mx_dim; t.mx_taps = e->tc_mx_taps;
@@ -844,7 +887,108 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
     t.net_ak[k] = ak;
   }
   for (int k = 0; k < PINN_MAX_TERMS; ++k) { t.seed[k] = a.seed[k]; t.dyn[k] = a.dyn[k]; }
+  t.tail = a.tail;
   CUDA_TRY(tc_launch(t, grid, e->smem, st));
+  return 0;
+}
+
+
+static bool any_sampler(const pinn_engine* e) {
+  for (int t = 0; t < e->n_terms; ++t) if (e->sampler_on[t]) return true;
+  return false;
+}
+
+// tail arguments of one step
+static void fill_tail(pinn_engine* e, TailArgs& t, const ScaleW& sw, void* out_grad, void* out_terms, void* out_total,
+                      bool adam, bool multi) {
+  memset(&t, 0, sizeof t);
+  t.state = e->d_state; t.out_grad = out_grad; t.out_terms = out_terms; t.out_total = out_total;
+  if (adam) {
+    t.adam_theta = e->d_theta; t.adam_m = e->adam_m; t.adam_v = e->adam_v;
+    t.adam_lr = e->adam_lr; t.adam_b1 = e->adam_b1; t.adam_b2 = e->adam_b2; t.adam_eps = e->adam_eps;
+    t.bump_draw = any_sampler(e) ? 1 : 0;
+  }
+  t.timeout_ns = e->tail_timeout_ns;
+  t.nranks = multi ? e->nranks : 1; t.rank = multi ? e->rank : 0;
+  t.terms_off = e->sym_terms_off;
+  if (multi)
+    for (int r = 0; r < e->nranks; ++r) {
+      char* b = (char*)e->peer_base[r];
+      t.peer_buf[0][r] = b; t.peer_buf[1][r] = b + e->sym_buf_bytes;
+      t.peer_flags[r] = (unsigned int*)(b + 2 * e->sym_buf_bytes);
+    }
+  t.sw = sw;
+}
+
+// One evaluation of the hot path on stream st: fused kernel (+ tail) and whatever follows it on this configuration.
+//   single GPU, or peer memory mapped:  ONE launch (tail reduces, sums over the peers, writes / applies Adam)
+//   multi-GPU without peer memory:      fused kernel (tail reduces into `packed`) -> ncclAllReduce -> finish_kernel
+//   PINN_B200_TAIL=0:                   fused kernel -> reduce_kernel [-> ncclAllReduce -> finish_kernel]   (round-1 sequence)
+static int eval_step(pinn_engine* e, const void* theta, const double* host_weights, void* out_grad, void* out_terms,
+                     void* out_total, bool adam, cudaStream_t st) {
+  const bool want_grad = adam || out_grad != nullptr;
+  FfmaArgs a;
+  memset(&a, 0, sizeof a);
+  fill_args(e, a, theta, want_grad ? 0 : 1);
+  ScaleW sw;
+  memset(&sw, 0, sizeof sw);
+  if (prepare_scales(e, host_weights, a, sw)) return 1;
+  const bool multi = e->nranks > 1;
+  int grid = std::min(e->num_sms, e->total_tiles);
+  if (multi && e->p2p) grid = e->num_sms;       // the same slice partition of theta on every rank
+  if (grid < 1) grid = 1;                       // a rank whose shard is empty still takes part in the reduction
+  if (grid > kTailSlots) return fail("pinn_loss_grad: %d CTAs exceed the %d tail slots", grid, kTailSlots);
+  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, st));
+  const long long ng = want_grad ? e->n_theta : 0;
+  char* pk = (char*)e->packed;
+  void* pk_terms = pk + (size_t)ng * e->es;
+  if (e->tail_on && (!multi || e->p2p)) {
+    fill_tail(e, a.tail, sw, out_grad, out_terms, out_total, adam, multi);
+    if (launch_fused(e, a, grid, st)) return 1;
+    if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
+    e->launches += 1;
+  } else {
+    if (adam && multi)
+      return fail("pinn_adam_iterate: the multi-GPU device loop needs the peer-memory allreduce (%s)",
+                  e->p2p_why[0] ? e->p2p_why : "not available");
+    if (e->tail_on) {
+      fill_tail(e, a.tail, sw, want_grad ? e->packed : nullptr, pk_terms, nullptr, false, false);
+      if (launch_fused(e, a, grid, st)) return 1;
+      if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
+      e->launches += 1;
+    } else {
+      if (launch_fused(e, a, grid, st)) return 1;
+      if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
+      e->launches += 1;
+      if (adam) {
+        e->adam_t += 1;
+        const double c1 = 1.0 - pow(e->adam_b1, (double)e->adam_t), c2 = sqrt(1.0 - pow(e->adam_b2, (double)e->adam_t));
+        CUDA_TRY(reduce_adam_launch(e->dtype, e->partial, e->partial_stride, e->term_sums, grid, e->n_theta, e->n_terms, sw, e->d_theta, e->adam_m,
+                                    e->adam_v, e->adam_lr * c2 / c1, e->adam_b1, e->adam_b2, e->adam_eps * c2, out_terms,
+                                    out_total, st));
+      } else if (multi) {
+        CUDA_TRY(reduce_launch(e->dtype, e->partial, e->partial_stride, e->term_sums, grid, e->n_theta, e->n_terms, sw, e->packed, pk_terms,
+                               nullptr, want_grad ? 1 : 0, st));
+      } else {
+        CUDA_TRY(reduce_launch(e->dtype, e->partial, e->partial_stride, e->term_sums, grid, e->n_theta, e->n_terms, sw, out_grad, out_terms,
+                               out_total, want_grad ? 1 : 0, st));
+      }
+      e->launches += 1;
+    }
+    if (multi) {
+      // packed = [grad (n_theta, zero-length when no gradient is wanted) | term losses]: one allreduce
+      ncclResult_t r = g_nccl.AllReduce(e->packed, e->packed, (size_t)ng + (size_t)e->n_terms,
+                                        e->dtype == PINN_F64 ? ncclFloat64 : ncclFloat32, ncclSumOp, e->comm, st);
+      if (r != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+      e->launches += 1;
+      CUDA_TRY(finish_launch(e->dtype, e->packed, ng, e->n_terms, sw, out_grad, out_terms, out_total, st));
+      e->launches += 1;
+    }
+  }
+  if (e->timing) {
+    CUDA_TRY(cudaEventSynchronize(e->ev1));
+    CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
+  }
   return 0;
 }
 
@@ -853,46 +997,11 @@ int pinn_loss_grad(pinn_handle e, const void* dev_theta, const double* host_weig
   if (!e) return fail("pinn_loss_grad: null handle");
   if (!dev_theta || !dev_term_losses || !dev_total) return fail("pinn_loss_grad: null theta/term_losses/total");
   CUDA_TRY(cudaSetDevice(e->device));
-  cudaStream_t st = (cudaStream_t)stream;
   for (int t = 0; t < e->n_terms; ++t)
     if (e->dyn[t].n <= 0 && !(e->nranks > 1 && e->n_global_set[t]))
       return fail("pinn_loss_grad: term %d has no points (call pinn_set_points first)", t);
-  if (e->total_tiles <= 0) return fail("pinn_loss_grad: no collocation points on this rank");
-  FfmaArgs a;
-  memset(&a, 0, sizeof a);
-  fill_args(e, a, dev_theta, dev_grad ? 0 : 1);
-  ScaleW sw;
-  memset(&sw, 0, sizeof sw);
-  if (prepare_scales(e, host_weights, a, sw)) return 1;
-  const int grid = std::min(e->num_sms, e->total_tiles);
-  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev0, st));
-  if (launch_fused(e, a, grid, st)) return 1;
-  if (e->timing) CUDA_TRY(cudaEventRecord(e->ev1, st));
-  e->launches += 1;
-  if (e->nranks > 1) {
-    // packed = [grad (n_theta, zero-length when no gradient is wanted) | term losses]: one allreduce
-    const long long ng = dev_grad ? e->n_theta : 0;
-    char* pk = (char*)e->packed;
-    void* pk_terms = pk + (size_t)ng * e->es;
-    CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, e->packed, pk_terms, nullptr,
-                           dev_grad ? 1 : 0, st));
-    e->launches += 1;
-    ncclResult_t r = g_nccl.AllReduce(e->packed, e->packed, (size_t)ng + (size_t)e->n_terms,
-                                      e->dtype == PINN_F64 ? ncclFloat64 : ncclFloat32, ncclSumOp, e->comm, st);
-    if (r != 0) return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
-    e->launches += 1;
-    CUDA_TRY(finish_launch(e->dtype, e->packed, ng, e->n_terms, sw, dev_grad, dev_term_losses, dev_total, st));
-    e->launches += 1;
-  } else {
-    CUDA_TRY(reduce_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, dev_grad,
-                           dev_term_losses, dev_total, dev_grad ? 1 : 0, st));
-    e->launches += 1;
-  }
-  if (e->timing) {
-    CUDA_TRY(cudaEventSynchronize(e->ev1));
-    CUDA_TRY(cudaEventElapsedTime(&e->last_ms, e->ev0, e->ev1));
-  }
-  return 0;
+  if (e->total_tiles <= 0 && e->nranks <= 1) return fail("pinn_loss_grad: no collocation points");
+  return eval_step(e, dev_theta, host_weights, dev_grad, dev_term_losses, dev_total, false, (cudaStream_t)stream);
 }
 
 int pinn_loss_grad_host(pinn_handle e, const void* host_theta, const double* host_weights, void* host_grad,
@@ -921,16 +1030,39 @@ int pinn_loss_grad_host(pinn_handle e, const void* host_theta, const double* hos
 int pinn_adam_begin(pinn_handle e, const void* host_theta0, double lr, double beta1, double beta2, double eps) {
   if (!e) return fail("pinn_adam_begin: null handle");
   if (!host_theta0) return fail("pinn_adam_begin: null theta");
-  if (e->nranks > 1) return fail("pinn_adam_begin: the fused Adam loop is single-GPU (use pinn_loss_grad + your optimizer)");
   CUDA_TRY(cudaSetDevice(e->device));
   const size_t tb = (size_t)e->n_theta * e->es;
   if (!e->adam_m) { if (dev_alloc(&e->adam_m, tb, e) || dev_alloc(&e->adam_v, tb, e)) return 1; }
   CUDA_TRY(cudaMemsetAsync(e->adam_m, 0, tb, e->own_stream));
   CUDA_TRY(cudaMemsetAsync(e->adam_v, 0, tb, e->own_stream));
+  CUDA_TRY(cudaMemsetAsync(&e->d_state->adam_t, 0, sizeof(unsigned long long), e->own_stream));
   CUDA_TRY(cudaMemcpyAsync(e->d_theta, host_theta0, tb, cudaMemcpyHostToDevice, e->own_stream));
   CUDA_TRY(cudaStreamSynchronize(e->own_stream));
   e->adam_lr = lr; e->adam_b1 = beta1; e->adam_b2 = beta2; e->adam_eps = eps; e->adam_t = 0; e->adam_ready = true;
   return 0;
+}
+
+static int draw_term(pinn_engine* e, int term, unsigned long long draw, const unsigned long long* draw_dev, cudaStream_t st);
+
+// one iteration of the device-resident loop: fresh points for the sampled terms, then the fused step with Adam in its tail
+static int enqueue_adam_iteration(pinn_engine* e, const double* host_weights, cudaStream_t st) {
+  char* dout = (char*)e->d_out;
+  if (any_sampler(e)) {
+    if (e->tail_on) {
+      // draw = host counter + 1 + device counter; the tail advances the device counter, so graph replays resample
+      for (int t = 0; t < e->n_terms; ++t)
+        if (e->sampler_on[t] && draw_term(e, t, e->sampler_draw + 1, &e->d_state->draw, st)) return 1;
+    } else if (pinn_resample(e, st)) {
+      return 1;
+    }
+  }
+  return eval_step(e, e->d_theta, host_weights, nullptr, dout, dout + (size_t)e->n_terms * e->es, true, st);
+}
+
+static unsigned long long fnv1a(const void* p, size_t n, unsigned long long h) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  return h;
 }
 
 int pinn_adam_iterate(pinn_handle e, int32_t n_steps, const double* host_weights, void* host_total, void* host_term_losses) {
@@ -938,27 +1070,46 @@ int pinn_adam_iterate(pinn_handle e, int32_t n_steps, const double* host_weights
   if (!e->adam_ready) return fail("pinn_adam_iterate: call pinn_adam_begin first");
   if (n_steps < 1) return fail("pinn_adam_iterate: n_steps must be >= 1");
   CUDA_TRY(cudaSetDevice(e->device));
-  if (e->total_tiles <= 0) return fail("pinn_adam_iterate: no collocation points");
+  if (e->total_tiles <= 0 && e->nranks <= 1) return fail("pinn_adam_iterate: no collocation points");
   cudaStream_t st = e->own_stream;
-  char* dout = (char*)e->d_out;
-  const int grid = std::min(e->num_sms, e->total_tiles);
-  bool any_sampler = false;
-  for (int t = 0; t < e->n_terms; ++t) any_sampler = any_sampler || e->sampler_on[t];
-  for (int it = 0; it < n_steps; ++it) {
-    if (any_sampler && pinn_resample(e, st)) return 1;      // fresh collocation points every step, drawn on the device
-    FfmaArgs a;
-    memset(&a, 0, sizeof a);
-    fill_args(e, a, e->d_theta, 0);
-    ScaleW sw;
-    memset(&sw, 0, sizeof sw);
-    if (prepare_scales(e, host_weights, a, sw)) return 1;
-    if (launch_fused(e, a, grid, st)) return 1;
-    e->adam_t += 1;
-    const double c1 = 1.0 - pow(e->adam_b1, (double)e->adam_t), c2 = sqrt(1.0 - pow(e->adam_b2, (double)e->adam_t));
-    CUDA_TRY(reduce_adam_launch(e->dtype, e->partial, e->term_sums, grid, e->n_theta, e->n_terms, sw, e->d_theta, e->adam_m,
-                                e->adam_v, e->adam_lr * c2 / c1, e->adam_b1, e->adam_b2, e->adam_eps * c2, dout,
-                                dout + (size_t)e->n_terms * e->es, st));
-    e->launches += 2;
+  const char* ng = getenv("PINN_B200_NO_GRAPH");
+  const bool use_graph = e->tail_on && (e->nranks <= 1 || e->p2p) && !e->timing && !(ng && ng[0] == '1');
+  if (use_graph) {
+    // the n_steps iterations are captured once into a CUDA graph (sampler draws + ONE fused launch per iteration) and
+    // replayed while the launch arguments stay the same: step counter, bias correction and draw counter live on the device
+    unsigned long long key = 1469598103934665603ull;
+    key = fnv1a(&n_steps, sizeof n_steps, key);
+    double w[PINN_MAX_TERMS];
+    for (int t = 0; t < PINN_MAX_TERMS; ++t) w[t] = (host_weights && t < e->n_terms) ? host_weights[t] : 1.0;
+    key = fnv1a(w, sizeof w, key);
+    key = fnv1a(e->dyn, sizeof e->dyn, key);
+    key = fnv1a(e->n_global, sizeof e->n_global, key);
+    const double hp[4] = {e->adam_lr, e->adam_b1, e->adam_b2, e->adam_eps};
+    key = fnv1a(hp, sizeof hp, key);
+    key = fnv1a(&e->sampler_draw, sizeof e->sampler_draw, key);
+    if (!e->adam_graph || e->adam_graph_key != key) {
+      if (e->adam_graph) { cudaGraphExecDestroy(e->adam_graph); e->adam_graph = nullptr; }
+      cudaGraph_t g = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+      int rc = 0;
+      const long long l0 = e->launches;
+      for (int it = 0; it < n_steps && !rc; ++it) rc = enqueue_adam_iteration(e, host_weights, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &g);
+      e->launches = l0;
+      if (rc) { if (g) cudaGraphDestroy(g); return 1; }
+      if (ce != cudaSuccess) return fail("pinn_adam_iterate: graph capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&e->adam_graph, g, 0);
+      cudaGraphDestroy(g);
+      if (ce != cudaSuccess) { e->adam_graph = nullptr; return fail("pinn_adam_iterate: graph instantiation failed: %s", cudaGetErrorString(ce)); }
+      e->adam_graph_key = key; e->adam_graph_n = n_steps;
+    }
+    CUDA_TRY(cudaGraphLaunch(e->adam_graph, st));
+    long long per_it = 1 + (e->tw ? 1 : 0);
+    for (int t = 0; t < e->n_terms; ++t) per_it += e->sampler_on[t] ? 1 : 0;
+    e->launches += per_it * n_steps;
+  } else {
+    for (int it = 0; it < n_steps; ++it)
+      if (enqueue_adam_iteration(e, host_weights, st)) return 1;
   }
   char* hout = (char*)e->h_pin_out;
   CUDA_TRY(cudaMemcpyAsync(hout, e->d_out, ((size_t)e->n_terms + 1) * e->es, cudaMemcpyDeviceToHost, st));
@@ -1014,12 +1165,13 @@ int pinn_term_residual_host(pinn_handle e, int32_t term, const void* host_theta,
   return rc;
 }
 
-static int draw_term(pinn_engine* e, int term, cudaStream_t st) {
+// effective draw index = draw + *draw_dev (the device counter is advanced by the tail of the device-resident loop)
+static int draw_term(pinn_engine* e, int term, unsigned long long draw, const unsigned long long* draw_dev, cudaStream_t st) {
   const int dim = e->hprob->terms[term].dim;
   const long long n = e->sampler_n[term];
   if (grow(&e->own_pts[term], &e->own_pts_cap[term], (size_t)n * dim * e->es, e)) return 1;
   CUDA_TRY(sample_uniform_launch(e->dtype, e->own_pts[term], n, dim, e->sampler_lb[term], e->sampler_ub[term],
-                                 e->sampler_seed[term] + 0x9E3779B97F4A7C15ull * (unsigned long long)(term + 1), e->sampler_draw, st));
+                                 e->sampler_seed[term] + 0x9E3779B97F4A7C15ull * (unsigned long long)(term + 1), draw, draw_dev, st));
   e->launches += 1;
   e->dyn[term].pts = e->own_pts[term]; e->dyn[term].qw = nullptr; e->dyn[term].n = n;
   return 0;
@@ -1039,7 +1191,7 @@ int pinn_set_sampler(pinn_handle e, int32_t term, int64_t n, const double* host_
     e->sampler_lb[term][r] = host_lb[r]; e->sampler_ub[term][r] = host_ub[r];
   }
   e->sampler_on[term] = true; e->sampler_seed[term] = seed; e->sampler_n[term] = n;
-  if (draw_term(e, term, (cudaStream_t)stream)) return 1;
+  if (draw_term(e, term, e->sampler_draw, &e->d_state->draw, (cudaStream_t)stream)) return 1;
   retile(e);
   return 0;
 }
@@ -1049,7 +1201,7 @@ int pinn_resample(pinn_handle e, void* stream) {
   CUDA_TRY(cudaSetDevice(e->device));
   e->sampler_draw += 1;
   for (int t = 0; t < e->n_terms; ++t)
-    if (e->sampler_on[t] && draw_term(e, t, (cudaStream_t)stream)) return 1;
+    if (e->sampler_on[t] && draw_term(e, t, e->sampler_draw, &e->d_state->draw, (cudaStream_t)stream)) return 1;
   retile(e);
   return 0;
 }
@@ -1105,10 +1257,95 @@ int pinn_comm_unique_id(void* out) {
   return 0;
 }
 
+// Map every rank's symmetric region [grad+terms buffer x 2 parities | per-slice flags] into this process so the fused
+// kernel's tail can add the peers' gradient slices straight over NVLink (tail.cuh).  Every rank runs the same two
+// collectives (handle allgather, agreement allreduce) whatever its local outcome; on any failure all ranks fall back to
+// ncclAllReduce together and p2p_why says why.
+struct PeerRec {
+  cudaIpcMemHandle_t handle;
+  char bus[32];
+  int ok;
+  int pad;
+};
+
+static int setup_p2p(pinn_engine* e) {
+  e->p2p = false;
+  int ok = 1;
+  auto why = [&](const char* msg) { if (!e->p2p_why[0]) snprintf(e->p2p_why, sizeof e->p2p_why, "%s", msg); ok = 0; };
+  if (!g_nccl.AllGather) { why("ncclAllGather not found"); return 0; }        // same library on every rank: uniform exit
+  const char* no = getenv("PINN_B200_NO_P2P");
+  if (no && no[0] == '1') why("disabled by PINN_B200_NO_P2P=1");
+  if (!e->tail_on) why("PINN_B200_TAIL=0");
+  if (e->nranks > kMaxRanks) why("more ranks than one NVSwitch domain (8)");
+  if (e->num_sms > kTailSlots) why("more SMs than tail slots");
+  const size_t gb = (((size_t)e->n_theta * e->es) + 255) & ~size_t(255);
+  e->sym_terms_off = (long long)gb;
+  e->sym_buf_bytes = (gb + PINN_MAX_TERMS * sizeof(double) + 255) & ~size_t(255);
+  const size_t flag_bytes = (size_t)kMaxRanks * kTailSlots * sizeof(unsigned int);
+  const size_t total = 2 * e->sym_buf_bytes + flag_bytes;
+  PeerRec mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok) {
+    if (cudaMalloc(&e->sym, total) != cudaSuccess) { e->sym = nullptr; why("cudaMalloc of the symmetric region failed"); }
+    else {
+      e->ws_bytes += (long long)total;
+      if (cudaMemset(e->sym, 0, total) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) why("symmetric region init failed");
+      else if (cudaIpcGetMemHandle(&mine.handle, e->sym) != cudaSuccess) why("cudaIpcGetMemHandle failed");
+      else if (cudaDeviceGetPCIBusId(mine.bus, sizeof mine.bus, e->device) != cudaSuccess) why("cudaDeviceGetPCIBusId failed");
+    }
+    cudaGetLastError();
+  }
+  mine.ok = ok;
+  PeerRec* d_recs = nullptr;
+  std::vector<PeerRec> recs((size_t)e->nranks);
+  CUDA_TRY(cudaMalloc((void**)&d_recs, sizeof(PeerRec) * e->nranks));
+  CUDA_TRY(cudaMemcpy(d_recs + e->rank, &mine, sizeof mine, cudaMemcpyHostToDevice));
+  ncclResult_t r = g_nccl.AllGather(d_recs + e->rank, d_recs, sizeof(PeerRec), ncclInt8, e->comm, (cudaStream_t)0);
+  if (r != 0) { cudaFree(d_recs); return fail("ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+  CUDA_TRY(cudaMemcpy(recs.data(), d_recs, sizeof(PeerRec) * e->nranks, cudaMemcpyDeviceToHost));
+  for (int q = 0; q < e->nranks; ++q) if (!recs[q].ok) why("a peer rank could not export its symmetric region");
+  if (ok) {
+    for (int q = 0; q < e->nranks && ok; ++q) {
+      if (q == e->rank) { e->peer_base[q] = e->sym; continue; }
+      int pdev = -1, can = 0;
+      if (cudaDeviceGetByPCIBusId(&pdev, recs[q].bus) != cudaSuccess) { why("a peer GPU is not visible to this process"); break; }
+      if (cudaDeviceCanAccessPeer(&can, e->device, pdev) != cudaSuccess || !can) { why("no peer access between the GPUs"); break; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, recs[q].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        why("cudaIpcOpenMemHandle failed (ranks in one process, or IPC unavailable)");
+        break;
+      }
+      e->peer_base[q] = ptr;
+    }
+    cudaGetLastError();
+  }
+  // agreement: the peer path is used only if every rank mapped every peer
+  int* d_ok = (int*)d_recs;
+  CUDA_TRY(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  r = g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMinOp, e->comm, (cudaStream_t)0);
+  if (r != 0) { cudaFree(d_recs); return fail("ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); }
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+  int all_ok = 0;
+  CUDA_TRY(cudaMemcpy(&all_ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(d_recs);
+  if (!all_ok && ok) why("a peer rank could not map the symmetric regions");
+  if (!all_ok) {
+    for (int q = 0; q < e->nranks; ++q)
+      if (q != e->rank && e->peer_base[q]) { cudaIpcCloseMemHandle(e->peer_base[q]); }
+    memset(e->peer_base, 0, sizeof e->peer_base);
+    cudaGetLastError();
+    return 0;
+  }
+  e->p2p = true;
+  return 0;
+}
+
 int pinn_comm_init(pinn_handle e, const void* uid, int32_t rank, int32_t nranks) {
   if (!e) return fail("pinn_comm_init: null handle");
   if (!uid) return fail("pinn_comm_init: null unique id");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail("pinn_comm_init: bad rank %d / nranks %d", rank, nranks);
+  if (e->comm) return fail("pinn_comm_init: the handle already has a communicator");
   if (!load_nccl()) return fail("pinn_comm_init: libnccl.so.2 could not be loaded: %s", dlerror());
   CUDA_TRY(cudaSetDevice(e->device));
   ncclUniqueId id;
@@ -1116,7 +1353,15 @@ int pinn_comm_init(pinn_handle e, const void* uid, int32_t rank, int32_t nranks)
   ncclResult_t r = g_nccl.CommInitRank(&e->comm, nranks, id, rank);
   if (r != 0) return fail("ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
   e->rank = rank; e->nranks = nranks;
+  if (nranks > 1 && setup_p2p(e)) return 1;
   return 0;
+}
+
+// which gradient-sum path pinn_loss_grad uses at nranks > 1: *fused_p2p = 1 when the sum runs inside the fused kernel over
+// peer memory, 0 when it falls back to ncclAllReduce (reason, if any, in the returned string; valid until the next call)
+const char* pinn_comm_info(pinn_handle e, int32_t* fused_p2p) {
+  if (fused_p2p) *fused_p2p = (e && e->p2p) ? 1 : 0;
+  return e ? e->p2p_why : "";
 }
 
 // diagnostic (not part of the drop-in ABI): enable phase timestamps of CTA 0 in the tcgen05 kernel and

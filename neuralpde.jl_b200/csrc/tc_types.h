@@ -35,7 +35,8 @@ struct TcNetSmem {
 struct TcArgs {
   const DevProblem* prob;
   const float* theta;
-  float* partial;         // [grid][n_theta]
+  float* partial;         // [grid][partial_stride]
+  long long partial_stride;
   double* term_sums;      // [grid][PINN_MAX_TERMS]
   uint8_t* stash;         // [grid][stash_per_cta] operand-tile images of every tensor layer's input
   long long stash_per_cta;
@@ -53,6 +54,7 @@ struct TcArgs {
   int net_ak[PINN_MAX_NETS];   // 1: every hidden activation is tanh (fast path), 0: generic
   double seed[PINN_MAX_TERMS];
   TermDyn dyn[PINN_MAX_TERMS];
+  TailArgs tail;
 };
 
 
@@ -73,7 +75,8 @@ constexpr int kTwMaxImages = PINN_MAX_NETS * kTcMaxTL;
 struct TwArgs {
   const DevProblem* prob;
   const float* theta;
-  float* partial;          // [grid][n_theta]
+  float* partial;          // [grid][partial_stride]
+  long long partial_stride;
   double* term_sums;       // [grid][PINN_MAX_TERMS]
   uint8_t* hstash;         // [grid][hstash_per_cta] bf16 operand tiles: input of tensor layer l, [slot][l-1][c][kb]
   long long hstash_per_cta;
@@ -95,6 +98,7 @@ struct TwArgs {
   int net_ak[PINN_MAX_NETS];
   double seed[PINN_MAX_TERMS];
   TermDyn dyn[PINN_MAX_TERMS];
+  TailArgs tail;
 };
 
 struct TwPackArgs {

@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <string.h>
 #include "tc_common.cuh"
+#include "tail.cuh"
 
 namespace pinn {
 
@@ -809,7 +810,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
   const DevProblem* Pp = args.prob;
   const DevProblem& P = *Pp;
   const Misc ms = misc_of(smem + args.off_misc, args.mx_dim, args.mx_taps);
-  float* partial = args.partial + (long long)blockIdx.x * P.n_theta;
+  float* partial = args.partial + (long long)blockIdx.x * args.partial_stride;
   const bool want_grad = (args.mode == 0);
   const float* theta = args.theta;
   long long span_c0 = 0;
@@ -1004,6 +1005,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
   }
   if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = ms.tsum[tid];
   if (warp == 0) tc::tmem_dealloc<512>(cs.tmem);
+  // gradient reduction, optimizer step and the multi-GPU sum in the kernel tail (tail.cuh)
+  if (args.tail.state)
+    fused_tail<float, kTcThreads>(args.tail, args.partial, args.partial_stride, args.term_sums, P.n_theta, P.n_terms, want_grad ? 1 : 0,
+                                  reinterpret_cast<float*>(smem + args.off_P));
 }
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------
@@ -1015,8 +1020,7 @@ cudaError_t tw_pack_launch(const TwPackArgs& a, cudaStream_t st) {
 cudaError_t tw_launch(const TwArgs& a, int grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(tw_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tw_loss_grad_kernel<<<grid, kTcThreads, smem, st>>>(a);
-  return cudaGetLastError();
+  return launch_fused_kernel(tw_loss_grad_kernel, a, grid, kTcThreads, smem, st, a.tail.state != nullptr);
 }
 
 }  // namespace pinn

@@ -37,6 +37,7 @@ EXPORTS = [
     "pinn_launch_count", "pinn_set_timing", "pinn_last_kernel_ms", "pinn_workspace_bytes",
     "pinn_flops_per_eval", "pinn_adam_begin", "pinn_adam_iterate", "pinn_adam_theta",
     "pinn_term_grad_stats", "pinn_term_grad_stats_host", "pinn_set_sampler", "pinn_resample", "pinn_get_points_host",
+    "pinn_comm_info",
 ]
 
 
@@ -163,6 +164,8 @@ def load_library():
     lib.pinn_comm_unique_id.restype = C.c_int
     lib.pinn_comm_init.argtypes = [vp, vp, i32, i32]
     lib.pinn_comm_init.restype = C.c_int
+    lib.pinn_comm_info.argtypes = [vp, C.POINTER(i32)]
+    lib.pinn_comm_info.restype = C.c_char_p
     lib.pinn_launch_count.argtypes = [vp]
     lib.pinn_launch_count.restype = i64
     lib.pinn_set_timing.argtypes = [vp, i32]
@@ -400,6 +403,13 @@ class Engine:
     def comm_init(self, unique_id: bytes, rank: int, nranks: int):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         _check(self.lib.pinn_comm_init(self._h, C.cast(buf, C.c_void_p), int(rank), int(nranks)))
+
+    def comm_info(self):
+        """(fused_p2p, reason): whether the multi-GPU gradient sum runs inside the fused kernel over peer memory,
+        and why not when it fell back to ncclAllReduce."""
+        flag = C.c_int32(0)
+        why = self.lib.pinn_comm_info(self._h, C.byref(flag))
+        return bool(flag.value), (why or b"").decode("utf-8", "replace")
 
     # -- introspection ------------------------------------------------------------------------------
     def launch_count(self) -> int:

@@ -48,11 +48,14 @@ class LoweredTerm:
             return pts
         if pts.shape[0] != len(self.indvars):
             raise ValueError("expected %d coordinate rows, got %d" % (len(self.indvars), pts.shape[0]))
-        syms = [sp.Symbol(v, real=True) for v in self.indvars]
         rows64 = [pts[i].astype(np.float64) for i in range(pts.shape[0])]
+        fns = getattr(self, "_extra_fns", None)
+        if fns is None:          # compiled once per term: resampling strategies call augment on every loss evaluation
+            syms = [sp.Symbol(v, real=True) for v in self.indvars]
+            fns = [sp.lambdify(syms, e, "numpy") for e in self.extra_exprs]
+            self._extra_fns = fns
         extra = []
-        for e in self.extra_exprs:
-            f = sp.lambdify(syms, e, "numpy")
+        for f in fns:
             extra.append(np.broadcast_to(np.asarray(f(*rows64), dtype=np.float64), rows64[0].shape))
         return np.concatenate([pts, np.stack(extra).astype(pts.dtype)], axis=0)
 

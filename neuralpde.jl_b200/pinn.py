@@ -101,25 +101,136 @@ class NonAdaptiveLoss:
     bc_loss_weights: Union[float, Sequence[float]] = 1.0
     additional_loss_weights: Union[float, Sequence[float]] = 1.0
 
+    def reweights_at(self, iteration: int) -> bool:
+        return False
+
     def update(self, iteration, pde_losses, bc_losses, weights, term_grad_stats=None):   # Returns(nothing)
         return None
 
 
 @dataclass
+class Adam:
+    """``Optimisers.Adam(η, (β1, β2), ϵ)`` hyper-parameters (also the rule of ``solve``)."""
+    lr: float = 1e-3
+    beta1: float = 0.9
+    beta2: float = 0.999
+    eps: float = 1e-8
+
+
+@dataclass
+class Descent:
+    """``Optimisers.Descent(η)``."""
+    lr: float = 0.1
+
+
+class _RuleState:
+    """``Optimisers.setup(rule, x)`` + ``Optimisers.update!(state, x, dx)`` for the two rules the adaptive losses use:
+    x .-= step(dx).  Adam: mt, vt moments with bias correction by running powers of β (Optimisers.jl's `apply!`)."""
+
+    def __init__(self, rule, n: int):
+        self.rule = rule
+        self.m, self.v = np.zeros(n), np.zeros(n)
+        self.b1t, self.b2t = 1.0, 1.0
+
+    def update(self, x: np.ndarray, dx: np.ndarray):
+        r = self.rule
+        dx = np.asarray(dx, dtype=np.float64)
+        if isinstance(r, Descent):
+            x -= r.lr * dx
+            return
+        self.b1t *= r.beta1
+        self.b2t *= r.beta2
+        self.m = r.beta1 * self.m + (1.0 - r.beta1) * dx
+        self.v = r.beta2 * self.v + (1.0 - r.beta2) * dx * dx
+        x -= self.m / (1.0 - self.b1t) / (np.sqrt(self.v / (1.0 - self.b2t)) + r.eps) * r.lr
+
+
+def _softmax(x: np.ndarray) -> np.ndarray:
+    e = np.exp(x - np.max(x))          # reference src/adaptive_losses.jl:242-245
+    return e / e.sum()
+
+
+@dataclass
 class MiniMaxAdaptiveLoss:
-    """Weights ascend on the per-term losses every ``reweight_every`` iterations
-    (reference src/adaptive_losses.jl:183-239; optimiser fixed to plain gradient ascent)."""
+    """Weights are MAXIMISED by an internal optimiser fed with ``-losses`` every ``reweight_every`` iterations
+    (reference src/adaptive_losses.jl:183-239; defaults ``Adam(1e-4)`` for the pde weights and ``Adam(0.5)`` for the
+    bc weights, any ``Adam(...)`` / ``Descent(...)`` rule accepted)."""
     reweight_every: int
-    pde_max_optimiser_lr: float = 1e-4
-    bc_max_optimiser_lr: float = 0.5
+    pde_max_optimiser: object = field(default_factory=lambda: Adam(1e-4))
+    bc_max_optimiser: object = field(default_factory=lambda: Adam(0.5))
     pde_loss_weights: Union[float, Sequence[float]] = 1.0
     bc_loss_weights: Union[float, Sequence[float]] = 1.0
     additional_loss_weights: Union[float, Sequence[float]] = 1.0
 
+    def reweights_at(self, iteration: int) -> bool:
+        return iteration % self.reweight_every == 0
+
     def update(self, iteration, pde_losses, bc_losses, weights, term_grad_stats=None):
+        if not hasattr(self, "_pde_state"):      # Optimisers.setup at generate_adaptive_loss_function time (:205-210)
+            self._pde_state = _RuleState(self.pde_max_optimiser, len(weights["pde"]))
+            self._bc_state = _RuleState(self.bc_max_optimiser, len(weights["bc"]))
         if iteration % self.reweight_every == 0:
-            weights["pde"] += self.pde_max_optimiser_lr * np.asarray(pde_losses, dtype=np.float64)
-            weights["bc"] += self.bc_max_optimiser_lr * np.asarray(bc_losses, dtype=np.float64)
+            self._pde_state.update(weights["pde"], -np.asarray(pde_losses, dtype=np.float64))
+            self._bc_state.update(weights["bc"], -np.asarray(bc_losses, dtype=np.float64))
+
+
+@dataclass
+class SoftAdaptAdaptiveLoss:
+    """``λ = softmax(α · (L(t) − L(t_prev)) / (L(t_prev) + ε)) · N`` over all pde and bc terms every ``reweight_every``
+    iterations (reference src/adaptive_losses.jl:247-364; Heydari et al., arXiv:1912.12355).  The previous losses are
+    seeded by the very first call (:335-339) and replaced at every reweighting."""
+    reweight_every: int
+    alpha: float = 0.1
+    pde_loss_weights: Union[float, Sequence[float]] = 1.0
+    bc_loss_weights: Union[float, Sequence[float]] = 1.0
+    additional_loss_weights: Union[float, Sequence[float]] = 1.0
+
+    def reweights_at(self, iteration: int) -> bool:
+        return iteration % self.reweight_every == 0
+
+    def update(self, iteration, pde_losses, bc_losses, weights, term_grad_stats=None):
+        cur = np.concatenate([np.asarray(pde_losses, dtype=np.float64), np.asarray(bc_losses, dtype=np.float64)])
+        if not hasattr(self, "_prev"):
+            self._prev = cur.copy()
+        if iteration % self.reweight_every == 0:
+            rates = (cur - self._prev) / (self._prev + 1e-8)
+            w = _softmax(self.alpha * rates) * cur.size
+            n_pde = len(pde_losses)
+            weights["pde"][:] = w[:n_pde]
+            weights["bc"][:] = w[n_pde:]
+            self._prev = cur.copy()
+
+
+@dataclass
+class ReLoBRaLoAdaptiveLoss:
+    """Relative loss balancing with random lookback: ``λ = softmax(α · L(t) / (L(t0) + ε)) · N`` where t0 is the
+    previous reweighting with probability β and the first call otherwise (reference src/adaptive_losses.jl:366-491;
+    Bischof & Kraus, arXiv:2110.09813).  ``seed`` fixes the Bernoulli draws (the reference uses the global RNG)."""
+    reweight_every: int
+    alpha: float = 1.0
+    beta: float = 0.9
+    pde_loss_weights: Union[float, Sequence[float]] = 1.0
+    bc_loss_weights: Union[float, Sequence[float]] = 1.0
+    additional_loss_weights: Union[float, Sequence[float]] = 1.0
+    seed: Optional[int] = None
+
+    def reweights_at(self, iteration: int) -> bool:
+        return iteration % self.reweight_every == 0
+
+    def update(self, iteration, pde_losses, bc_losses, weights, term_grad_stats=None):
+        cur = np.concatenate([np.asarray(pde_losses, dtype=np.float64), np.asarray(bc_losses, dtype=np.float64)])
+        if not hasattr(self, "_init"):
+            self._init, self._prev = cur.copy(), cur.copy()
+            self._rng = np.random.default_rng(self.seed)
+        if iteration % self.reweight_every == 0:
+            use_prev = self._rng.random() < self.beta
+            ref = self._prev if use_prev else self._init
+            w = _softmax(self.alpha * cur / (ref + 1e-8)) * cur.size
+            n_pde = len(pde_losses)
+            weights["pde"][:] = w[:n_pde]
+            weights["bc"][:] = w[n_pde:]
+            self._prev = cur.copy()
+            self.last_use_prev = bool(use_prev)
 
 
 @dataclass
@@ -133,6 +244,9 @@ class GradientScaleAdaptiveLoss:
     pde_loss_weights: Union[float, Sequence[float]] = 1.0
     bc_loss_weights: Union[float, Sequence[float]] = 1.0
     additional_loss_weights: Union[float, Sequence[float]] = 1.0
+
+    def reweights_at(self, iteration: int) -> bool:
+        return iteration % self.reweight_every == 0
 
     def update(self, iteration, pde_losses, bc_losses, weights, term_grad_stats=None):
         if iteration % self.reweight_every != 0:
@@ -485,14 +599,24 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
     logger, log_frequency = d.logger, d.log_options.log_frequency
 
     def _evaluate(theta, want_grad: bool):
+        """src/discretize.jl:567-598: term losses, iteration += 1, reweight, THEN the weighted sum -- the returned loss
+        and gradient use the weights the reweighting just produced.  On a reweighting iteration that takes a loss-only
+        evaluation first (a third of a step); every other iteration is a single fused call."""
         resample()
         state["calls"] += 1
-        total, terms, grad = eng.loss_grad_host(np.asarray(theta, dtype=dtype), term_weights(), want_grad)
+        th = np.asarray(theta, dtype=dtype)
+        stats = lambda i: eng.term_grad_stats_host(i, th)           # noqa: E731
+        it = iteration[0] + 1 if d.self_increment else iteration[0]   # :574-576
+        if adaloss.reweights_at(it):
+            _, terms0, _ = eng.loss_grad_host(th, term_weights(), False)
+            iteration[0] = it
+            adaloss.update(it, terms0[:n_pde], terms0[n_pde:n_pde + n_bc], weights, term_grad_stats=stats)   # :578-580
+            total, terms, grad = eng.loss_grad_host(th, term_weights(), want_grad)
+        else:
+            total, terms, grad = eng.loss_grad_host(th, term_weights(), want_grad)
+            iteration[0] = it
+            adaloss.update(it, terms[:n_pde], terms[n_pde:n_pde + n_bc], weights, term_grad_stats=stats)
         pde_losses, bc_losses = terms[:n_pde], terms[n_pde:n_pde + n_bc]
-        if d.self_increment:
-            iteration[0] += 1                     # src/discretize.jl:574-576
-        adaloss.update(iteration[0], pde_losses, bc_losses, weights,   # :578-580 (outside the gradient)
-                       term_grad_stats=lambda i: eng.term_grad_stats_host(i, np.asarray(theta, dtype=dtype)))
         if logger is not None and iteration[0] % log_frequency == 0:  # :600-645
             it = iteration[0]
             logvector(logger, pde_losses, "unweighted_loss/pde_losses", it)
@@ -559,6 +683,9 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
     def set_points(i: int, pts, w=None, n_global: Optional[int] = None):
         """Replace term i's point set ((d, N) coordinates; hoisted rows are appended here)."""
         point_sets[i] = np.asarray(pts, dtype=dtype)
+        if world > 1 and n_global is None:
+            raise ValueError("set_points on a sharded problem replaces this rank's shard: pass n_global (the term's "
+                             "point count over all ranks) so the mean is scaled correctly")
         upload(i, point_sets[i], w, shard=False)
         if n_global is not None:
             eng.set_global_count(i, n_global)
@@ -592,14 +719,6 @@ def discretize(pde_system: PDESystem, discretization: PhysicsInformedNN, rank: i
 
 
 @dataclass
-class Adam:
-    lr: float = 1e-3
-    beta1: float = 0.9
-    beta2: float = 0.999
-    eps: float = 1e-8
-
-
-@dataclass
 class Solution:
     u: np.ndarray
     objective: float
@@ -624,12 +743,34 @@ def solve(prob: OptimizationProblem, opt: Adam, maxiters: int = 100, callback: O
         eng = rep.engine
         eng.adam_begin(prob.u0, opt.lr, opt.beta1, opt.beta2, opt.eps)
         done, obj = 0, float("nan")
-        w = np.concatenate([rep.weights["pde"], rep.weights["bc"]] +
-                           ([rep.weights["add"]] if rep.additional_loss is not None else []))
+        adaloss, weights, iteration = rep.adaloss, rep.weights, rep.iteration
+        n_pde, n_bc = len(rep.eqs), len(rep.bcs)
+
+        def term_w():
+            return np.concatenate([weights["pde"], weights["bc"]] + ([weights["add"]] if rep.additional_loss is not None else []))
+
+        adaptive = not isinstance(adaloss, NonAdaptiveLoss)
         while done < maxiters:
             n = min(chunk, maxiters - done)
-            obj, _ = eng.adam_iterate(n, w)
+            if adaptive:
+                # iterations up to (not including) the next reweighting run on the device with the current weights; the
+                # reweighting iteration reads theta back once, evaluates the term losses, updates the weights
+                # (src/discretize.jl:574-588 order) and takes its step with the new ones
+                nxt = (iteration[0] // adaloss.reweight_every + 1) * adaloss.reweight_every
+                n = min(n, max(nxt - iteration[0] - 1, 0))
+                if n == 0:
+                    th = eng.adam_theta()
+                    _, terms0, _ = eng.loss_grad_host(th, term_w(), False)
+                    iteration[0] += 1
+                    adaloss.update(iteration[0], terms0[:n_pde], terms0[n_pde:n_pde + n_bc], weights,
+                                   term_grad_stats=lambda i: eng.term_grad_stats_host(i, th))
+                    n = 1
+                    iteration[0] -= 1
+            obj, terms = eng.adam_iterate(n, term_w())
+            if adaptive and n > 0 and not hasattr(adaloss, "_seen_first"):
+                adaloss._seen_first = True
             done += n
+            iteration[0] += n
             if callback is not None and callback({"iter": done, "u": None}, obj):
                 break
         return Solution(eng.adam_theta(), obj, done)

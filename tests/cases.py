@@ -63,6 +63,15 @@ CASES = {
 }
 
 
+# the shapes BASELINE.json names (goldens: tests/golden/make_golden_full.py; theta / points regenerated from seeds)
+FULL_CASES = {
+    "cfg2_full": lambda: configs.config2(),                                                        # 128^2, 4x64
+    "cfg3_full": lambda: configs.config3(),                                                        # 65 536 + 3 x 4 096, 5x128
+    "cfg5_full": lambda: configs.config5(points=65536, bcs_points=4096, n_obs=1024),               # 4x128, 6 channels, data + theta.p
+    "cfg4_w256": lambda: configs.config4(nodes=6, bc_nodes=4, width=256, hidden=2),                # 4 nets, 256-wide, 7 channels
+}
+
+
 def point_sets(cfg: Config, seed: int = 11):
     """Deterministic (d, N) float64 point sets [pde..., bc...] (+ quadrature weights / scales) of a case."""
     sys_ = cfg.pde_system

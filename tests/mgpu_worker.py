@@ -1,5 +1,6 @@
-"""Worker for tests/test_gpu_multi.py: each rank evaluates its shard on its own GPU; the engine all-reduces
-[grad | term losses] over NCCL.  Launched with torch.distributed.run."""
+"""Worker for tests/test_gpu_multi.py: each rank evaluates its shard on its own GPU; the gradient and the term losses are
+summed over the ranks inside the fused kernel over peer memory (or by ncclAllReduce with PINN_B200_NO_P2P=1), then a
+few steps of the device-resident Adam loop run on every rank.  Launched with torch.distributed.run."""
 import os
 import sys
 
@@ -26,7 +27,22 @@ dist.broadcast_object_list(uid, src=0)
 rep.engine.comm_init(uid[0], rank, world)
 tot, terms, g = rep.engine.loss_grad_host(rep.flat_init_params, None, True)
 tot2, terms2, _ = rep.engine.loss_grad_host(rep.flat_init_params, None, False)      # loss-only path of the allreduce
+fused, why = rep.engine.comm_info()
+# device-resident Adam over the ranks (peer-memory path only): every rank must end with the same theta bit for bit
+th_adam, adam_loss = np.zeros(0), float("nan")
+if fused:
+    rep.engine.adam_begin(rep.flat_init_params, 1e-3)
+    rep.engine.adam_iterate(3)
+    adam_loss, _ = rep.engine.adam_iterate(3)           # second call replays the captured graph
+    th_adam = rep.engine.adam_theta()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, th_adam.tobytes())
+    assert all(b == gathered[0] for b in gathered), "replicas diverged"
+# repeated evaluations: the flag / parity protocol over many steps
+for _ in range(20):
+    tot3, _, g3 = rep.engine.loss_grad_host(rep.flat_init_params, None, True)
 if rank == 0:
-    np.savez(out, tot=tot, terms=terms, g=g, tot2=tot2, terms2=terms2)
+    np.savez(out, tot=tot, terms=terms, g=g, tot2=tot2, terms2=terms2, fused=int(fused), why=why, th_adam=th_adam,
+             adam_loss=adam_loss, tot3=tot3, g3=g3)
 dist.barrier()
 dist.destroy_process_group()

@@ -99,3 +99,42 @@ def test_param_estim_gradient_entry():
     rep, total, terms, grad = engine_eval_sets(CASES["cfg5_small"](), np.float64, sets, qw, theta=g["theta"])
     assert abs(grad[-1] - g["grad"][-1]) <= 1e-9 * abs(g["grad"][-1]) and abs(g["grad"][-1]) > 0
     assert len(terms) == len(g["terms"]) == 1 + 5 + 1          # pde + 5 bcs + data loss
+
+
+# ---- the shapes BASELINE.json names (tests/golden/make_golden_full.py) -------------------------------------------------------
+from cases import FULL_CASES, point_sets      # noqa: E402
+
+
+def _full(name):
+    import hashlib
+    g = np.load(__import__("os").path.join(__import__("os").path.dirname(__import__("os").path.abspath(__file__)), "golden", name + ".npz"))
+    cfg = FULL_CASES[name]()
+    theta = cfg.init_params(np.float64, seed=1)
+    sets, qw, qs = point_sets(cfg)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a, dtype=np.float64).tobytes()).hexdigest()      # noqa: E731
+    assert sha(theta) == str(g["theta_sha"]) and sha(sets[0]) == str(g["set0_sha"]), "regenerated inputs differ from the golden's"
+    return g, cfg, theta, sets, qw
+
+
+@pytest.mark.parametrize("name,mode,ltol,gtol", [
+    ("cfg2_full", "tc_split", 1e-5, 1e-2),     # the headline kernel at the headline shape: 128^2 + 4 x 128 points, 4x64
+    ("cfg2_full", "tc_bf16", 1e-2, 2e-2),
+    ("cfg2_full", "ffma", 1e-5, 5e-4),
+    ("cfg3_full", "tc_bf16", 1e-2, 2e-2),      # 128-wide kernel, 65 536 + 3 x 4 096 points, 5x128: 608 dynamically claimed tiles
+    ("cfg3_full", "ffma", 1e-5, 5e-4),
+    ("cfg5_full", "tc_bf16", 1e-2, 2e-2),      # 4x128, 6 channels -> two passes, data loss + theta.p, 65 536 points
+    ("cfg5_full", "ffma", 1e-5, 5e-4),
+    ("cfg4_w256", "ffma", 1e-5, 5e-4),         # 4 coupled networks, 256-wide layers, 7 channels, quadrature weights
+])
+def test_full_shape_matches_oracle(name, mode, ltol, gtol):
+    """Loss, per-term losses and gradient against the float64 oracle at the shapes BASELINE.json names.  Stated tolerances:
+    FFMA fp32 loss 1e-5 / gradient 5e-4; tc_split loss 1e-5 / gradient 1e-2 (its reverse sweep uses bf16 operands);
+    tc_bf16 loss 1e-2 / gradient 2e-2."""
+    g, cfg, theta, sets, qw = _full(name)
+    rep, total, terms, grad = engine_eval_sets(cfg, np.float32, sets, qw, mode=mode, theta=theta)
+    L = float(g["total"])
+    err, gerr = abs(total - L) / abs(L), rel(grad, g["grad"])
+    print("%s %s: loss rel %.3e grad rel %.3e" % (name, mode, err, gerr))
+    assert err <= ltol, (total, L)
+    np.testing.assert_allclose(terms, g["terms"], rtol=max(10 * ltol, 1e-4), atol=1e-12)
+    assert gerr < gtol

@@ -89,9 +89,21 @@ def test_term_grad_stats_and_gradient_scale_adaptive_loss():
     disc.adaptive_loss = ada
     rep2 = npde.symbolic_discretize(cfg.pde_system, disc)
     f = rep2.loss_functions.full_loss_function
-    f(th)                                    # iteration 1: no reweighting
-    f(th)                                    # iteration 2: reweights after the evaluation
-    expected = 0.5 * 1.0 + 0.5 * stats[0][0] / (np.array([s_[1] for s_ in stats[1:]]) + 1e-7)
-    total3 = f(th)                           # evaluated with the new boundary weights
     terms = rep.engine.loss_grad_host(th, None, False)[1]
-    assert abs(total3 - (terms[0] + float(np.dot(expected, terms[1:])))) <= 1e-10 * abs(total3)
+    total1 = f(th)                           # iteration 1: no reweighting
+    assert abs(total1 - float(np.sum(terms))) <= 1e-12 * abs(total1)
+    # iteration 2 reweights BEFORE forming the weighted sum (src/discretize.jl:574-588): the returned loss already uses
+    # the new boundary weights
+    total2 = f(th)
+    expected = 0.5 * 1.0 + 0.5 * stats[0][0] / (np.array([s_[1] for s_ in stats[1:]]) + 1e-7)
+    assert abs(total2 - (terms[0] + float(np.dot(expected, terms[1:])))) <= 1e-10 * abs(total2)
+    total3 = f(th)                           # iteration 3: same weights, no reweighting
+    assert abs(total3 - total2) <= 1e-12 * abs(total2)
+    # the gradient of a reweighting iteration uses the new weights too
+    wfull = np.concatenate([[1.0], expected])
+    _, _, g_expected = rep.engine.loss_grad_host(th, wfull, True)
+    disc_b = cfg.discretization(dtype=np.float64)
+    disc_b.adaptive_loss = npde.GradientScaleAdaptiveLoss(1, weight_change_inertia=0.5)
+    rep_b = npde.symbolic_discretize(cfg.pde_system, disc_b)
+    tot_b, g_b = rep_b.loss_functions.full_loss_gradient(th)          # iteration 1 is already a reweighting iteration
+    assert abs(tot_b - total2) <= 1e-10 * abs(total2) and rel(g_b, g_expected) < 1e-12

@@ -171,6 +171,63 @@ def test_gradient_scale_adaptive_loss_rule():
     np.testing.assert_allclose(w["pde"], [1.0, 1.0])
 
 
+def test_minimax_adaptive_loss_uses_the_optimiser_rule():
+    """reference src/adaptive_losses.jl:192-195, :223-237: Optimisers.update!(setup(Adam(lr)), weights, -losses).  The first
+    Adam step moves every weight by ~lr whatever the loss magnitude (m / sqrt(v) = sign), the second follows the moment
+    recursion; Descent(lr) is plain ascent."""
+    ada = npde.MiniMaxAdaptiveLoss(2)
+    assert ada.pde_max_optimiser.lr == 1e-4 and ada.bc_max_optimiser.lr == 0.5
+    w = {"pde": np.ones(1), "bc": np.array([1.0, 3.0]), "add": np.ones(1)}
+    ada.update(1, [10.0], [1e-3, 7.0], w)
+    np.testing.assert_allclose(w["bc"], [1.0, 3.0]); np.testing.assert_allclose(w["pde"], [1.0])
+    ada.update(2, [10.0], [1e-3, 7.0], w)
+    np.testing.assert_allclose(w["pde"], [1.0 + 1e-4], rtol=1e-9)
+    np.testing.assert_allclose(w["bc"], [1.5, 3.5], rtol=1e-4)          # eps = 1e-8 against |g| = 1e-3 shows at 1e-5
+    g1, g2 = np.array([-1e-3, -7.0]), np.array([-2e-3, -1.0])
+    ada.update(4, [10.0], -g2, w)
+    m = 0.9 * (0.1 * g1) + 0.1 * g2
+    v = 0.999 * (0.001 * g1 ** 2) + 0.001 * g2 ** 2
+    step = 0.5 * (m / (1 - 0.9 ** 2)) / (np.sqrt(v / (1 - 0.999 ** 2)) + 1e-8)
+    np.testing.assert_allclose(w["bc"], np.array([1.0, 3.0]) + 0.5 * (0.1 * -g1 / 0.1) / (np.sqrt(0.001 * g1 ** 2 / 0.001) + 1e-8) - step,
+                               rtol=1e-12)
+    asc = npde.MiniMaxAdaptiveLoss(1, pde_max_optimiser=npde.Descent(0.1), bc_max_optimiser=npde.Descent(0.5))
+    w2 = {"pde": np.ones(1), "bc": np.ones(2), "add": np.ones(1)}
+    asc.update(1, [2.0], [4.0, 6.0], w2)
+    np.testing.assert_allclose(w2["pde"], [1.2]); np.testing.assert_allclose(w2["bc"], [3.0, 4.0])
+
+
+def test_softadapt_and_relobralo_rules():
+    """reference src/adaptive_losses.jl:330-361 (SoftAdapt: softmax(alpha * relative change since the last reweighting) * N)
+    and :461-488 (ReLoBRaLo: softmax(alpha * L / L_ref) * N with L_ref = previous reweighting w.p. beta, else the first call)."""
+    def softmax(x):
+        e = np.exp(x - x.max()); return e / e.sum()
+    sa = npde.SoftAdaptAdaptiveLoss(2, alpha=0.1)
+    w = {"pde": np.ones(1), "bc": np.ones(2), "add": np.ones(1)}
+    L1, L2, L3 = np.array([4.0, 1.0, 0.5]), np.array([2.0, 1.5, 0.5]), np.array([1.0, 3.0, 0.25])
+    sa.update(1, L1[:1], L1[1:], w)                       # seeds prev, no reweighting
+    np.testing.assert_allclose(np.r_[w["pde"], w["bc"]], 1.0)
+    sa.update(2, L2[:1], L2[1:], w)
+    np.testing.assert_allclose(np.r_[w["pde"], w["bc"]], softmax(0.1 * (L2 - L1) / (L1 + 1e-8)) * 3, rtol=1e-13)
+    sa.update(3, L3[:1], L3[1:], w)                       # not a reweighting iteration: prev stays L2
+    sa.update(4, L3[:1], L3[1:], w)
+    np.testing.assert_allclose(np.r_[w["pde"], w["bc"]], softmax(0.1 * (L3 - L2) / (L2 + 1e-8)) * 3, rtol=1e-13)
+    assert abs(w["pde"].sum() + w["bc"].sum() - 3.0) < 1e-12
+    for beta, ref in ((0.0, L1), (1.0, L2)):              # beta = 0: always the initial losses; beta = 1: always the previous
+        rl = npde.ReLoBRaLoAdaptiveLoss(1, alpha=1.0, beta=beta, seed=0)
+        w = {"pde": np.ones(1), "bc": np.ones(2), "add": np.ones(1)}
+        rl.update(1, L1[:1], L1[1:], w)
+        np.testing.assert_allclose(np.r_[w["pde"], w["bc"]], softmax(L1 / (L1 + 1e-8)) * 3, rtol=1e-13)
+        rl.update(2, L2[:1], L2[1:], w)
+        rl.update(3, L3[:1], L3[1:], w)
+        np.testing.assert_allclose(np.r_[w["pde"], w["bc"]], softmax(L3 / (ref + 1e-8)) * 3, rtol=1e-13)
+    rl = npde.ReLoBRaLoAdaptiveLoss(1, beta=0.5, seed=123)
+    w = {"pde": np.ones(1), "bc": np.ones(2), "add": np.ones(1)}
+    draws = []
+    for it, L in enumerate([L1, L2, L3, L1, L2, L3, L1, L2], start=1):
+        rl.update(it, L[:1], L[1:], w); draws.append(rl.last_use_prev)
+    assert any(draws) and not all(draws)                  # both references occur at beta = 0.5
+
+
 def _run_ir(prog, rows, taps):
     """Evaluate a lowered residual program on the host (rows: point-matrix rows incl. hoisted ones)."""
     val = []
