@@ -52,33 +52,37 @@ def _deps_mtime() -> float:
     return m
 
 
-def _extra_units():
-    """Optional translation units (tcgen05 path) picked up when present."""
+def _extra_units(debug: bool):
+    """tcgen05 translation units; the descriptor probe (tc_probe.cu) only in debug builds."""
     extra = []
     for f in sorted(os.listdir(CSRC)):
-        if f.startswith("tc_") and f.endswith(".cu"):
+        if f.startswith("tc_") and f.endswith(".cu") and (debug or f != "tc_probe.cu"):
             extra.append((f[:-3] + ".o", f, []))
     return extra
 
 
-def build(verbose: bool = False, force: bool = False, tc_threads: int = 0) -> str:
-    """tc_threads != 0 builds an experimental variant library (libpinn_b200_t<N>.so) of the tcgen05 kernel."""
-    global OBJDIR, LIB
-    if tc_threads and "build_x" not in OBJDIR and "build_d" not in OBJDIR:
-        OBJDIR = os.path.join(HERE, "build_t%d" % tc_threads)
-        LIB = os.path.join(LIBDIR, "libpinn_b200_t%d.so" % tc_threads)
-        NVCC_FLAGS.append("-DPINN_TC_THREADS=%d" % tc_threads)
+def build(verbose: bool = False, force: bool = False, defines=(), debug: bool = False) -> str:
+    """Default: the product library lib/libpinn_b200.so (no instrumentation).
+    debug=True: lib/libpinn_b200_debug.so with -DPINN_DEBUG (phase timestamps for scripts/tc_timeline.py, the tcgen05
+    descriptor probe for scripts/tc_probe*.py).  defines=("NAME=VAL", ...): a measurement variant
+    lib/libpinn_b200_<tag>.so built in build_<tag>/ (select it with PINN_B200_LIB)."""
+    objdir, lib, flags = OBJDIR, LIB, list(NVCC_FLAGS)
+    tag = ("debug" if debug else "") + "".join(d.replace("=", "") for d in defines)
+    if tag:
+        objdir = os.path.join(HERE, "build_" + tag)
+        lib = os.path.join(LIBDIR, "libpinn_b200_%s.so" % tag)
+        flags += ["-D" + d for d in defines] + (["-DPINN_DEBUG"] if debug else [])
     os.makedirs(LIBDIR, exist_ok=True)
-    os.makedirs(OBJDIR, exist_ok=True)
+    os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     hdr_m = _deps_mtime()
-    units = UNITS + _extra_units()
+    units = UNITS + _extra_units(debug)
     jobs = []
     for obj, src, defs in units:
-        o = os.path.join(OBJDIR, obj)
+        o = os.path.join(objdir, obj)
         s = os.path.join(CSRC, src)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_m):
-            jobs.append([nvcc, *NVCC_FLAGS, *defs, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
+            jobs.append([nvcc, *flags, *defs, "-c", s, "-o", o] + (["-Xptxas", "-v"] if verbose else []))
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -91,23 +95,15 @@ def build(verbose: bool = False, force: bool = False, tc_threads: int = 0) -> st
                     sys.stderr.write(r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError("nvcc failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
-    objs = [os.path.join(OBJDIR, u[0]) for u in units]
-    if jobs or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-ldl"]
+    objs = [os.path.join(objdir, u[0]) for u in units]
+    if jobs or not os.path.exists(lib) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs, "-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed: %s\n%s\n%s" % (" ".join(cmd), r.stdout, r.stderr))
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    for a in sys.argv:
-        if a.startswith("-D"):      # experimental define: -DPINN_TC_GW=2 -> libpinn_b200_dPINN_TC_GW2.so
-            tag = a[2:].replace("=", "")
-            OBJDIR = os.path.join(HERE, "build_d" + tag); LIB = os.path.join(LIBDIR, "libpinn_b200_d%s.so" % tag)
-            NVCC_FLAGS.append(a)
-        if a.startswith("-X"):      # timing experiments: -XNO_LDTM etc. -> libpinn_b200_x<name>.so
-            OBJDIR = os.path.join(HERE, "build_x" + a[2:]); LIB = os.path.join(LIBDIR, "libpinn_b200_x%s.so" % a[2:])
-            NVCC_FLAGS.append("-DPINN_EXP_" + a[2:])
-    tt = [int(a[2:]) for a in sys.argv if a.startswith("-t")]
-    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, tc_threads=tt[0] if tt else 0))
+    print(build(verbose="-v" in sys.argv, force="-f" in sys.argv, debug="--debug" in sys.argv,
+                defines=tuple(a[2:] for a in sys.argv if a.startswith("-D"))))

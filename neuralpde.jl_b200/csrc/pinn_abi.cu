@@ -1364,6 +1364,7 @@ const char* pinn_comm_info(pinn_handle e, int32_t* fused_p2p) {
   return e ? e->p2p_why : "";
 }
 
+#ifdef PINN_DEBUG
 // diagnostic (not part of the drop-in ABI): enable phase timestamps of CTA 0 in the tcgen05 kernel and
 // read them back (2000 x int64: [0,1000) phase marks id << 48 | clock, [1000,2000) per-CTA
 // {globaltimer start, end, cycles, smid}); host_out == NULL only enables.
@@ -1380,6 +1381,7 @@ int pinn_debug_tc_timeline(pinn_handle e, long long* host_out) {
   }
   return 0;
 }
+#endif
 
 int64_t pinn_launch_count(pinn_handle e) { return e ? e->launches : 0; }
 int pinn_set_timing(pinn_handle e, int32_t enable) {

@@ -58,6 +58,16 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ float4 ld_relaxed_sys_v(const float4* p) {
+  float4 v;
+  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double2 ld_relaxed_sys_v(const double2* p) {
+  double2 v;
+  asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned long long tail_now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -218,7 +228,8 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
   if (!multi) return;
 
   // ---- 4. one-shot allreduce over peer memory: signal slice `bid` to every peer, wait for theirs, add in rank order -------
-  __threadfence_system();
+  // (the release store orders this CTA's slice, made visible to the signalling thread by the barrier, before the flag:
+  //  no CTA-wide system fence)
   __syncthreads();
   if (tid < ta.nranks && tid != ta.rank) {
     st_release_sys(ta.peer_flags[tid] + (size_t)ta.rank * kTailSlots + bid, step1);
@@ -227,11 +238,21 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
   }
   __syncthreads();
   if (want_grad) {
-    for (long long i = i0 + tid; i < i1; i += NT) {
-      real t = real(0);
-      for (int r = 0; r < ta.nranks; ++r)
-        t += ld_relaxed_sys(reinterpret_cast<const real*>(ta.peer_buf[s_step & 1u][r]) + i);
-      consume(i, t);
+    for (long long i = i0 + (long long)V * tid; i < i1; i += (long long)V * NT) {
+      real acc[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) acc[j] = real(0);
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)          // all peers' 16-byte loads in flight together, added in rank order
+        if (r < ta.nranks) {
+          const vec_t v = ld_relaxed_sys_v(reinterpret_cast<const vec_t*>(reinterpret_cast<const real*>(ta.peer_buf[s_step & 1u][r]) + i));
+          const real* pv = reinterpret_cast<const real*>(&v);
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[j] += pv[j];
+        }
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (i + j < i1) consume(i + j, acc[j]);
     }
   }
   if (bid == 0 && tid == 0) {

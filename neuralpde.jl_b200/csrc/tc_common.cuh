@@ -261,11 +261,14 @@ __device__ __forceinline__ int reduceg_elem(int lane) { return GW == 4 ? reduce4
 __device__ __forceinline__ bool reduceg_lead(int lane) { return GW == 4 ? ((lane & 7) == 0) : ((lane & 15) == 0); }
 
 // phase timestamps for the timeline tool (scripts/tc_timeline.py): id in the high bits, clock in the low
+// (only in -DPINN_DEBUG builds: libpinn_b200_debug.so; the product library carries no instrumentation)
 template <typename CS>
 __device__ __forceinline__ void dbg_mark(CS* cs, int id) {
+#ifdef PINN_DEBUG
   if (cs->dbg && threadIdx.x == 0 && cs->dbg_n < 1000) {
     cs->dbg[cs->dbg_n++] = ((long long)id << 48) | (clock64() & 0xffffffffffffLL);
   }
+#endif
 }
 
 struct Misc {   // carve-up of the misc region

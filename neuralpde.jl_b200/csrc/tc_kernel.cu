@@ -729,12 +729,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
   float* partial = args.partial + (long long)blockIdx.x * args.partial_stride;
   const bool want_grad = (args.mode == 0);
   const float* theta = args.theta;
+#ifdef PINN_DEBUG
   long long span_c0 = 0;
   unsigned long long span_g0 = 0;
   if (args.dbg && tid == 0) {
     span_c0 = clock64();
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(span_g0));
   }
+#endif
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------------------------
   if (tid == 0) {
@@ -746,10 +748,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     cs.partial = partial;
     cs.stash = args.stash + (long long)blockIdx.x * args.stash_per_cta;
     cs.theta = theta;
+#ifdef PINN_DEBUG
     cs.dbg = (blockIdx.x == 0) ? args.dbg : nullptr;
+#else
+    cs.dbg = nullptr;
+#endif
     cs.dbg_n = 0;
     for (int k = 0; k < PINN_MAX_NETS; ++k) cs.nets[k] = args.nets[k];
+#ifdef PINN_DEBUG
     if (cs.dbg) cs.dbg[cs.dbg_n++] = ((long long)1 << 48) | (clock64() & 0xffffffffffffLL);
+#endif
   }
   if (warp == 0) tc::tmem_alloc<512>(ms.tmem_slot);
   if (want_grad) {
@@ -929,6 +937,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
   tc::tc_fence_before();
   __syncthreads();
   dbg_mark(&cs, 7);
+#ifdef PINN_DEBUG
   if (tid == 0 && cs.dbg) cs.dbg[999] = cs.dbg_n;
   if (args.dbg && tid == 0 && blockIdx.x < 250) {
     unsigned long long g1;
@@ -938,6 +947,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     long long* rec = args.dbg + 1000 + 4 * blockIdx.x;
     rec[0] = (long long)span_g0; rec[1] = (long long)g1; rec[2] = clock64() - span_c0; rec[3] = smid;
   }
+#endif
   if (tid < PINN_MAX_TERMS) args.term_sums[(long long)blockIdx.x * PINN_MAX_TERMS + tid] = ms.tsum[tid];
   if (warp == 0) tc::tmem_dealloc<512>(cs.tmem);
   // gradient reduction, optimizer step and the multi-GPU sum in the kernel tail (tail.cuh)

@@ -1,4 +1,6 @@
 """Sweep tcgen05 descriptor hypotheses on the GPU (uses pinn_debug_mma_probe)."""
+import os
+os.environ.setdefault("PINN_B200_LIB", os.path.join("neuralpde.jl_b200", "lib", "libpinn_b200_debug.so"))   # build.py --debug
 import ctypes as C, itertools, sys
 import numpy as np
 sys.path.insert(0, ".")
