@@ -199,30 +199,33 @@ def subsample(sets, quad, frac: float):
 
 
 def best_thread_count(cfg, theta64, sets, quad, cores: int) -> int:
-    """The reference side gets the thread count that serves it best (oversubscribing small GEMMs on a
-    many-core host is slower than using fewer threads)."""
-    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    """The reference side gets the thread count that serves it best ON THE SAMPLE IT IS TIMED ON (oversubscribing small
+    GEMMs on a many-core host is slower than using fewer threads; the optimum moves with the sample size)."""
+    cands = sorted({c for c in (8, 16, 32, 64) if c <= cores} or {cores})
+    cpu_reference_eval(cfg, theta64, sets, cands[0], 1, quad)          # warm-up (allocator, MKL thread pool)
     best, best_t = cands[0], float("inf")
     for c in cands:
-        cpu_reference_eval(cfg, theta64, sets, c, 1, quad)
-        _, t, _ = cpu_reference_eval(cfg, theta64, sets, c, 2, quad)
-        if min(t) < best_t:
-            best, best_t = c, min(t)
+        _, t, _ = cpu_reference_eval(cfg, theta64, sets, c, 1, quad)
+        if t[0] < best_t:
+            best, best_t = c, t[0]
+        if t[0] > 1.5 * best_t:
+            break                                                       # past the optimum
     return best
 
 
 def timed_cpu_sample(cfg, theta64, sets, quad, budget_s: float, reps: int):
-    """Bounded sample of the workload for the CPU arm: a probe on 1/64 of the points sizes the fraction that fits
-    `budget_s` seconds for `reps` evaluations."""
+    """Bounded sample of the workload for the CPU arm: a probe on a small leading fraction sizes the fraction that fits
+    `budget_s` seconds for `reps` evaluations; the thread count is then chosen on that sample."""
     cores_all = os.cpu_count() or 1
-    probe_s, probe_q = subsample(sets, quad, min(1.0, max(1.0 / 64, 512.0 / max(s.shape[1] for s in sets))))
-    cores = best_thread_count(cfg, theta64, probe_s, probe_q, cores_all)
-    _, tp, _ = cpu_reference_eval(cfg, theta64, probe_s, cores, 1, probe_q)
+    probe_s, probe_q = subsample(sets, quad, min(1.0, max(1.0 / 64, 2048.0 / max(s.shape[1] for s in sets))))
+    cpu_reference_eval(cfg, theta64, probe_s, min(16, cores_all), 1, probe_q)
+    _, tp, _ = cpu_reference_eval(cfg, theta64, probe_s, min(16, cores_all), 1, probe_q)
     n_probe = sum(s.shape[1] for s in probe_s)
     n_full = sum(s.shape[1] for s in sets)
     per_pt = tp[0] / n_probe
-    frac = min(1.0, budget_s / max(reps * per_pt * n_full, 1e-9))
+    frac = min(1.0, budget_s / max((reps + 5) * per_pt * n_full, 1e-9))
     s2, q2 = subsample(sets, quad, frac)
+    cores = best_thread_count(cfg, theta64, s2, q2, cores_all)
     return cores, s2, q2
 
 

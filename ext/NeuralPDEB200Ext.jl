@@ -16,7 +16,7 @@ import NeuralPDE: PhysicsInformedNN, AbstractPINN, PINNRepresentation, GridTrain
 const lib = "libpinn_b200"
 
 # ---- C mirrors of include/pinn_b200.h ----------------------------------------------------------------------------------
-const PINN_ABI_VERSION = Cint(1)
+const PINN_ABI_VERSION = Cint(2)
 const PINN_MAX_IN = 8
 const PINN_F32, PINN_F64 = Cint(0), Cint(1)
 const PINN_MODE_FFMA, PINN_MODE_TC_BF16, PINN_MODE_TC_SPLIT = Cint(0), Cint(1), Cint(2)
@@ -33,7 +33,7 @@ struct PinnNet
     n_layers::Cint; dims::Ptr{Cint}; acts::Ptr{Cint}; theta_offset::Int64
 end
 struct PinnTap
-    net::Cint; out::Cint; order::Cint; dir::NTuple{2, Cint}
+    net::Cint; out::Cint; order::Cint; dir::NTuple{4, Cint}
 end
 struct PinnTerm
     dim::Cint; n_taps::Cint; taps::Ptr{PinnTap}; net_rows::Ptr{Cint}; n_instr::Cint; prog::Ptr{PinnInstr}
@@ -154,7 +154,8 @@ function lower_expr!(L::Lowered, ex, env)
         cord, εs, order = ex.args[4], ex.args[5], Int(ex.args[6])
         dirs = [findfirst(!iszero, ε) - 1 for ε in εs]
         length(dirs) == order || throw(ArgumentError("NeuralPDEB200Ext: derivative order $order with $(length(dirs)) directions"))
-        order <= 2 || throw(ArgumentError("NeuralPDEB200Ext: derivative orders above 2 are not supported by the engine"))
+        (order <= 2 || (order == 3 && allequal(dirs))) ||
+            throw(ArgumentError("NeuralPDEB200Ext: the engine takes derivatives up to order 2 and pure third derivatives"))
         return tap!(L, net_of(cord, env), order, dirs)
     end
     f, args = if ex.head === :. && ex.args[2] isa Expr && ex.args[2].head === :tuple
@@ -255,7 +256,7 @@ function lower(pinnrep::PINNRepresentation, chains, mode::Cint)
     terms = PinnTerm[]
     for fn in vcat(pinnrep.symbolic_pde_loss_functions, pinnrep.symbolic_bc_loss_functions)
         L = lower_loss_function(fn, depvars; default_p = pinnrep.default_p)
-        taps = [PinnTap(t[1], 0, t[2], (Cint(get(t[3], 1, 0)), Cint(get(t[3], 2, 0)))) for t in L.taps]
+        taps = [PinnTap(t[1], 0, t[2], (Cint(get(t[3], 1, 0)), Cint(get(t[3], 2, 0)), Cint(get(t[3], 3, 0)), Cint(0))) for t in L.taps]
         rows = fill(Cint(-1), length(chains) * PINN_MAX_IN)
         for (k, r) in L.net_rows, (j, v) in enumerate(r)
             rows[k * PINN_MAX_IN + j] = v

@@ -53,12 +53,12 @@
 extern "C" {
 #endif
 
-#define PINN_ABI_VERSION 1
+#define PINN_ABI_VERSION 2
 
 /* hard limits (validated by pinn_create) */
 #define PINN_MAX_LAYERS 16   /* Dense layers per network */
 #define PINN_MAX_IN 8        /* network input dimension */
-#define PINN_MAX_CH 10       /* propagated channels per (term, network): 1 + #first + #second */
+#define PINN_MAX_CH 10       /* propagated channels per (term, network): 1 + #first + #second + #third */
 #define PINN_MAX_NETS 8
 #define PINN_MAX_TAPS 32     /* taps per term */
 #define PINN_MAX_INSTR 192   /* residual-program length per term */
@@ -140,8 +140,8 @@ typedef struct {
 typedef struct {
   int32_t net;     /* network (depvar) index                               */
   int32_t out;     /* output component of the network (0 for 1-output nets) */
-  int32_t order;   /* 0, 1 or 2                                            */
-  int32_t dir[2];  /* derivative directions (order 1: dir[0]; order 2: both) */
+  int32_t order;   /* 0, 1, 2 (any pair of directions) or 3 (pure: d^3/dx_i^3, PINN_MODE_FFMA) */
+  int32_t dir[4];  /* derivative directions, `order` entries used            */
 } pinn_tap_desc;
 
 enum { PINN_REDUCE_MEAN = 0, /* mean(abs2, r)            training_strategies.jl:220 */
@@ -223,6 +223,13 @@ int pinn_term_residual_host(pinn_handle h, int32_t term, const void* host_theta,
  * (callbacks, tests).  The random stream necessarily differs from Julia's default RNG; the distribution is the same. */
 int pinn_set_sampler(pinn_handle h, int32_t term, int64_t n, const double* host_lb, const double* host_ub, uint64_t seed,
                      void* stream);
+/* QuasiRandomTraining on the device: kind = PINN_SAMPLER_LHS draws a Latin hypercube sample per call -- the reference's
+ * default `sampling_alg = LatinHypercubeSample()` (src/training_strategies.jl:285-334; QuasiMonteCarlo.sample on the host
+ * + upload per call, :365-389).  Each row's n strata hold exactly one point per draw: stratum index = a keyed Feistel
+ * permutation of the point index, position inside the stratum uniform (Philox).  pinn_set_sampler == kind UNIFORM. */
+enum { PINN_SAMPLER_UNIFORM = 0, PINN_SAMPLER_LHS = 1 };
+int pinn_set_sampler_ex(pinn_handle h, int32_t term, int32_t kind, int64_t n, const double* host_lb, const double* host_ub,
+                        uint64_t seed, void* stream);
 int pinn_resample(pinn_handle h, void* stream);
 int pinn_get_points_host(pinn_handle h, int32_t term, void* host_pts);
 

@@ -31,8 +31,11 @@ struct DevNet {
 //   channel 0            value
 //   channels 1..n1       first derivatives along dir1[i]
 //   channels n1+1..      second derivatives d^2/(d dir1[s_a] d dir1[s_b])
+//   channels n1+n2+1..   pure third derivatives d^3/(d dir1[t_a])^3 (t_s: the pure second-derivative channel along the same
+//                        direction, which the chain rule of the third needs)
 struct DevChan {
-  int C, n1, n2;
+  int C, n1, n2, n3;
+  int t_a[PINN_MAX_IN], t_s[PINN_MAX_IN];
   int dir1[PINN_MAX_IN];
   int s_a[PINN_MAX_CH], s_b[PINN_MAX_CH];   // indices into dir1[] (0-based)
   int rows[PINN_MAX_IN];                    // point row feeding network input j
@@ -100,9 +103,8 @@ struct TailArgs {
   unsigned long long timeout_ns;   // spin bound of the barriers (a lost peer traps instead of hanging)
   int bump_draw;                   // advance state->draw (device-side samplers present)
   int nranks, rank;
-  long long terms_off;             // byte offset of the double[PINN_MAX_TERMS] term-loss block inside a peer buffer
-  void* peer_buf[2][kMaxRanks];    // symmetric [grad | term losses] buffers, by step parity, of every rank (peer-mapped)
-  unsigned int* peer_flags[kMaxRanks];   // [kMaxRanks][kTailSlots] flags of every rank (peer-mapped)
+  long long recv_words;            // 8-byte slots per (parity, source rank) block: n_theta words + 2 per term loss
+  void* peer_recv[kMaxRanks];      // receive region of every rank (peer-mapped): [2 parities][nranks][recv_words] slots
   ScaleW sw;
 };
 

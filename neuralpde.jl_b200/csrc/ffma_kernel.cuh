@@ -73,31 +73,35 @@ __device__ __forceinline__ real m_sigmoid(real z) {
   return e / (real(1) + e);
 }
 
-// activation value and its first three derivatives at z
+// activation value and its first four derivatives at z (the fourth enters the reverse sweep through third-derivative taps)
 template <typename real>
-__device__ __forceinline__ void act_eval(int act, real z, real& a, real& d1, real& d2, real& d3) {
+__device__ __forceinline__ void act_eval4(int act, real z, real& a, real& d1, real& d2, real& d3, real& d4) {
   switch (act) {
     case PINN_ACT_TANH: {
       real t = m_tanh(z);
       real s = real(1) - t * t;
       a = t; d1 = s; d2 = real(-2) * t * s; d3 = s * (real(6) * t * t - real(2));
+      d4 = real(8) * t * s * (real(2) - real(3) * t * t);
     } break;
     case PINN_ACT_SIGMOID: {
       real g = m_sigmoid(z);
       real g1 = g * (real(1) - g);
       real q = real(1) - real(2) * g;
-      a = g; d1 = g1; d2 = g1 * q; d3 = g1 * q * q - real(2) * g1 * g1;
+      real g2 = g1 * q;
+      real g3 = g2 * q - real(2) * g1 * g1;
+      a = g; d1 = g1; d2 = g2; d3 = g3; d4 = g3 * q - real(6) * g1 * g2;
     } break;
     case PINN_ACT_SIN: {
       real s = m_sin(z), c = m_cos(z);
-      a = s; d1 = c; d2 = -s; d3 = -c;
+      a = s; d1 = c; d2 = -s; d3 = -c; d4 = s;
     } break;
     case PINN_ACT_SOFTPLUS: {
       real g = m_sigmoid(z);
       real g1 = g * (real(1) - g);
       real q = real(1) - real(2) * g;
+      real g2 = g1 * q;
       a = (z > real(0)) ? z + m_log1p(m_exp(-z)) : m_log1p(m_exp(z));
-      d1 = g; d2 = g1; d3 = g1 * q;
+      d1 = g; d2 = g1; d3 = g2; d4 = g2 * q - real(2) * g1 * g1;
     } break;
     case PINN_ACT_SWISH: {
       real g = m_sigmoid(z);
@@ -105,11 +109,17 @@ __device__ __forceinline__ void act_eval(int act, real z, real& a, real& d1, rea
       real q = real(1) - real(2) * g;
       real g2 = g1 * q;
       real g3 = g2 * q - real(2) * g1 * g1;
-      a = z * g; d1 = g + z * g1; d2 = real(2) * g1 + z * g2; d3 = real(3) * g2 + z * g3;
+      real g4 = g3 * q - real(6) * g1 * g2;
+      a = z * g; d1 = g + z * g1; d2 = real(2) * g1 + z * g2; d3 = real(3) * g2 + z * g3; d4 = real(4) * g3 + z * g4;
     } break;
     default:
-      a = z; d1 = real(1); d2 = real(0); d3 = real(0);
+      a = z; d1 = real(1); d2 = real(0); d3 = real(0); d4 = real(0);
   }
+}
+template <typename real>
+__device__ __forceinline__ void act_eval(int act, real z, real& a, real& d1, real& d2, real& d3) {
+  real d4;
+  act_eval4<real>(act, z, a, d1, d2, d3, d4);
 }
 
 template <typename real> struct Cfg {
@@ -309,6 +319,12 @@ __device__ __forceinline__ void elementwise_fwd(real* Z, real* stash, const DevC
       for (int c = 0; c < C; ++c) stash[(c * n_out + o) * kTilePts + lane] = Z[c * ldc + idx];
     real a, d1, d2, d3;
     act_eval<real>(act, Z[idx], a, d1, d2, d3);
+    for (int q = 0; q < ch.n3; ++q) {       // pure third derivatives first: they read the pre-activations of the lower orders
+      real z1 = Z[(1 + ch.t_a[q]) * ldc + idx];
+      real z2 = Z[(n1 + 1 + ch.t_s[q]) * ldc + idx];
+      real z3 = Z[(n1 + n2 + 1 + q) * ldc + idx];
+      Z[(n1 + n2 + 1 + q) * ldc + idx] = d1 * z3 + real(3) * d2 * z1 * z2 + d3 * z1 * z1 * z1;
+    }
     for (int s = 0; s < n2; ++s) {
       real zs = Z[(n1 + 1 + s) * ldc + idx];
       real za = Z[(1 + ch.s_a[s]) * ldc + idx];
@@ -330,8 +346,8 @@ __device__ __forceinline__ void elementwise_bwd(real* B, const real* stash, cons
     const int idx = o * TP + lane;
     const int sidx = o * kTilePts + lane;
     const int cs = n_out * kTilePts;  // channel stride in the stash
-    real a, d1, d2, d3;
-    act_eval<real>(act, stash[sidx], a, d1, d2, d3);
+    real a, d1, d2, d3, d4;
+    act_eval4<real>(act, stash[sidx], a, d1, d2, d3, d4);
     real acc0 = d1 * B[idx];
     for (int i = 0; i < n1; ++i) {
       real zi = stash[(1 + i) * cs + sidx];
@@ -349,6 +365,15 @@ __device__ __forceinline__ void elementwise_bwd(real* B, const real* stash, cons
       B[ca * ldc + idx] += d2 * zb * hb;
       B[cb * ldc + idx] += d2 * za * hb;
       B[cq * ldc + idx] = d1 * hb;
+    }
+    for (int q = 0; q < ch.n3; ++q) {       // h3 = d1 z3 + 3 d2 z1 z2 + d3 z1^3
+      const int c1 = 1 + ch.t_a[q], c2 = n1 + 1 + ch.t_s[q], c3 = n1 + n2 + 1 + q;
+      real z1 = stash[c1 * cs + sidx], z2 = stash[c2 * cs + sidx], z3 = stash[c3 * cs + sidx];
+      real hb = B[c3 * ldc + idx];
+      acc0 += (d2 * z3 + real(3) * d3 * z1 * z2 + d4 * z1 * z1 * z1) * hb;
+      B[c1 * ldc + idx] += real(3) * (d2 * z2 + d3 * z1 * z1) * hb;
+      B[c2 * ldc + idx] += real(3) * d2 * z1 * hb;
+      B[c3 * ldc + idx] = d1 * hb;
     }
     B[idx] = acc0;
   }
@@ -373,6 +398,11 @@ __device__ __forceinline__ void rebuild_h(real* H, const real* stash, const DevC
       real za = stash[(1 + ch.s_a[s]) * cs + sidx];
       real zb = stash[(1 + ch.s_b[s]) * cs + sidx];
       H[(n1 + 1 + s) * ldc + idx] = d1 * zs + d2 * za * zb;
+    }
+    for (int q = 0; q < ch.n3; ++q) {
+      real z1 = stash[(1 + ch.t_a[q]) * cs + sidx], z2 = stash[(n1 + 1 + ch.t_s[q]) * cs + sidx];
+      real z3 = stash[(n1 + n2 + 1 + q) * cs + sidx];
+      H[(n1 + n2 + 1 + q) * ldc + idx] = d1 * z3 + real(3) * d2 * z1 * z2 + d3 * z1 * z1 * z1;
     }
   }
 }

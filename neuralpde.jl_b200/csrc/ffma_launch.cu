@@ -251,6 +251,69 @@ __global__ void __launch_bounds__(256) sample_uniform_kernel(real* pts, long lon
   }
 }
 
+// ---- device-side Latin hypercube sampler (QuasiRandomTraining's default sampling_alg = LatinHypercubeSample()) -----------
+// Row r of point i is lb_r + (ub_r - lb_r) * (pi_r(i) + u) / n with pi_r a keyed permutation of [0, n) and u uniform in
+// [0, 1): each of the n strata of every row holds exactly one point per draw.  pi_r is a 4-round Feistel network over
+// ceil(log2 n) bits (each round XORs one half with a hash of the other: a bijection) with cycle walking back into [0, n):
+// stateless, O(1) per point, no sort and no shuffle buffer.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint32_t feistel_perm(uint32_t i, uint32_t n, uint32_t bits, uint32_t k0, uint32_t k1) {
+  const uint32_t hb = bits >> 1, ob = bits - hb;
+  const uint32_t ma = (1u << hb) - 1u, mb = (1u << ob) - 1u;      // bits >= 2 here
+  uint32_t x = i;
+  do {
+    uint32_t a = x & ma, b = x >> hb;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      a ^= mix32(b + k0 + 0x9E3779B9u * (uint32_t)(2 * r + 1)) & ma;
+      b ^= mix32(a + k1 + 0x9E3779B9u * (uint32_t)(2 * r + 2)) & mb;
+    }
+    x = (b << hb) | a;
+  } while (x >= n);
+  return x;
+}
+
+template <typename real>
+__global__ void __launch_bounds__(256) sample_lhs_kernel(real* pts, long long n, int dim, SampleBox box, unsigned long long seed,
+                                                          unsigned long long draw, const unsigned long long* draw_dev) {
+  const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (p >= n) return;
+  if (draw_dev) draw += *draw_dev;
+  uint32_t bits = 2;
+  while ((1ull << bits) < (unsigned long long)n) ++bits;
+  for (int r = 0; r < dim; ++r) {
+    // per (row, draw) permutation key and per (point, row, draw) jitter from Philox
+    uint32_t kc[4] = {(uint32_t)r, (uint32_t)draw, (uint32_t)(draw >> 32), 0x4C48535Fu};
+    philox4x32_10(kc, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t c[4] = {(uint32_t)p, (uint32_t)(p >> 32), (uint32_t)r ^ ((uint32_t)draw << 8), (uint32_t)(draw >> 24) ^ 0x80000000u};
+    philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const double u = (double)((((unsigned long long)c[0] << 32) | c[1]) >> 11) * (1.0 / 9007199254740992.0);
+    double x;
+    if (n == 1) {
+      x = u;
+    } else {
+      const uint32_t j = feistel_perm((uint32_t)p, (uint32_t)n, bits, kc[0], kc[1]);
+      x = ((double)j + u) / (double)n;
+    }
+    pts[p * dim + r] = (real)(box.lb[r] + (box.ub[r] - box.lb[r]) * x);
+  }
+}
+
+cudaError_t sample_lhs_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
+                              unsigned long long seed, unsigned long long draw, const unsigned long long* draw_dev,
+                              cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  SampleBox box;
+  for (int r = 0; r < PINN_MAX_DIM; ++r) { box.lb[r] = r < dim ? lb[r] : 0.0; box.ub[r] = r < dim ? ub[r] : 0.0; }
+  const int blocks = (int)((n + 255) / 256);
+  if (dtype == PINN_F64) sample_lhs_kernel<double><<<blocks, 256, 0, st>>>((double*)pts, n, dim, box, seed, draw, draw_dev);
+  else sample_lhs_kernel<float><<<blocks, 256, 0, st>>>((float*)pts, n, dim, box, seed, draw, draw_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t sample_uniform_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
                                   unsigned long long seed, unsigned long long draw, const unsigned long long* draw_dev,
                                   cudaStream_t st) {

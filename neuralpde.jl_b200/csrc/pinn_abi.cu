@@ -26,6 +26,9 @@ cudaError_t grad_stats_launch(int dtype, const void* grad, long long n, double* 
 cudaError_t sample_uniform_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
                                   unsigned long long seed, unsigned long long draw, const unsigned long long* draw_dev,
                                   cudaStream_t st);
+cudaError_t sample_lhs_launch(int dtype, void* pts, long long n, int dim, const double* lb, const double* ub,
+                              unsigned long long seed, unsigned long long draw, const unsigned long long* draw_dev,
+                              cudaStream_t st);
 cudaError_t finish_launch(int dtype, const void* packed, long long n_grad, int n_terms, const ScaleW& scale_w, void* out_grad,
                           void* out_terms, void* out_total, cudaStream_t st);
 cudaError_t reduce_adam_launch(int dtype, const void* partial, long long stride, const double* term_sums, int nb, long long n_theta,
@@ -147,6 +150,7 @@ struct pinn_engine {
   bool adam_ready = false;
   // device-side samplers (StochasticTraining): per term box, seed, point count; draw counter shared by all terms
   bool sampler_on[PINN_MAX_TERMS];
+  int sampler_kind[PINN_MAX_TERMS];
   double sampler_lb[PINN_MAX_TERMS][PINN_MAX_DIM], sampler_ub[PINN_MAX_TERMS][PINN_MAX_DIM];
   unsigned long long sampler_seed[PINN_MAX_TERMS];
   long long sampler_n[PINN_MAX_TERMS];
@@ -162,11 +166,11 @@ struct pinn_engine {
   // comm
   ncclComm_t comm = nullptr;
   int rank = 0, nranks = 1;
-  // peer-memory allreduce (NVLink): symmetric region = [buf parity 0 | buf parity 1 | flags], mapped from every rank
+  // peer-memory allreduce (NVLink): receive region [2 parities][nranks][recv_words] of 8-byte {word, flag} slots,
+  // mapped from every rank
   bool p2p = false;
   void* sym = nullptr;
-  size_t sym_buf_bytes = 0;
-  long long sym_terms_off = 0;
+  long long recv_words = 0;
   void* peer_base[kMaxRanks];
   char p2p_why[160];
   // introspection
@@ -280,7 +284,7 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
         slot_of[tp.net] = T.n_used;
         T.used_net[T.n_used] = tp.net;
         DevChan& ch = T.chan[T.n_used];
-        ch.C = 1; ch.n1 = 0; ch.n2 = 0;
+        ch.C = 1; ch.n1 = 0; ch.n2 = 0; ch.n3 = 0;
         const int din = P.nets[tp.net].dims[0];
         for (int j = 0; j < din; ++j) {
           int r = td.net_rows[tp.net * PINN_MAX_IN + j];
@@ -297,8 +301,12 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
         const pinn_tap_desc& tp = td.taps[i];
         const int din = P.nets[tp.net].dims[0];
         DevChan& ch = T.chan[slot_of[tp.net]];
-        if (tp.order < 0 || tp.order > 2)
-          return fail("pinn_create: term %d tap %d has derivative order %d; orders 0..2 are supported", t, i, tp.order);
+        if (tp.order < 0 || tp.order > 3)
+          return fail("pinn_create: term %d tap %d has derivative order %d; orders 0..3 are supported (order 4 and mixed "
+                      "third derivatives are not)", t, i, tp.order);
+        if (tp.order == 3 && !(tp.dir[0] == tp.dir[1] && tp.dir[1] == tp.dir[2]))
+          return fail("pinn_create: term %d tap %d is a mixed third derivative; only pure third derivatives d^3/dx_i^3 are "
+                      "supported", t, i);
         if (tp.out < 0 || tp.out >= P.nets[tp.net].dims[P.nets[tp.net].n_layers])
           return fail("pinn_create: term %d tap %d output component %d out of range", t, i, tp.out);
         for (int q = 0; q < tp.order; ++q)
@@ -311,16 +319,26 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
             for (int j = 0; j < ch.n1; ++j) if (ch.dir1[j] == tp.dir[q]) found = j;
             if (found < 0) ch.dir1[ch.n1++] = tp.dir[q];
           }
-        } else if (tp.order == 2) {
+        } else if (tp.order >= 2) {
+          // order 3 (pure) needs the pure second derivative along the same direction as an intermediate
           int a = -1, b = -1;
           for (int j = 0; j < ch.n1; ++j) { if (ch.dir1[j] == tp.dir[0]) a = j; if (ch.dir1[j] == tp.dir[1]) b = j; }
           if (a > b) std::swap(a, b);
           int found = -1;
           for (int s = 0; s < ch.n2; ++s) if (ch.s_a[s] == a && ch.s_b[s] == b) found = s;
           if (found < 0) {
-            if (1 + ch.n1 + ch.n2 >= PINN_MAX_CH)
+            if (1 + ch.n1 + ch.n2 + ch.n3 >= PINN_MAX_CH)
               return fail("pinn_create: term %d network %d needs more than %d channels", t, tp.net, PINN_MAX_CH);
             ch.s_a[ch.n2] = a; ch.s_b[ch.n2] = b; ++ch.n2;
+          }
+          if (tp.order == 3) {
+            int ft = -1;
+            for (int q = 0; q < ch.n3; ++q) if (ch.t_a[q] == a) ft = q;
+            if (ft < 0) {
+              if (1 + ch.n1 + ch.n2 + ch.n3 >= PINN_MAX_CH)
+                return fail("pinn_create: term %d network %d needs more than %d channels", t, tp.net, PINN_MAX_CH);
+              ch.t_a[ch.n3++] = a;
+            }
           }
         }
       }
@@ -345,11 +363,16 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       }
       ch.pure = (npure == ch.n2) ? 1 : 0;
       if (ch.pure) for (int q = 0; q < ch.n2; ++q) ch.s_a[q] = ch.s_b[q] = q;
+      for (int q = 0; q < ch.n3; ++q) {
+        ch.t_a[q] = inv[ch.t_a[q]];
+        ch.t_s[q] = -1;
+        for (int q2 = 0; q2 < ch.n2; ++q2) if (ch.s_a[q2] == ch.t_a[q] && ch.s_b[q2] == ch.t_a[q]) ch.t_s[q] = q2;
+      }
     }
     long long stash = 0;
     for (int s = 0; s < T.n_used; ++s) {
       DevChan& ch = T.chan[s];
-      ch.C = 1 + ch.n1 + ch.n2;
+      ch.C = 1 + ch.n1 + ch.n2 + ch.n3;
       if (ch.C > PINN_MAX_CH) return fail("pinn_create: term %d needs %d channels (max %d)", t, ch.C, PINN_MAX_CH);
       maxC = std::max(maxC, ch.C);
       const DevNet& n = P.nets[T.used_net[s]];
@@ -369,12 +392,16 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
       else if (tp.order == 1) {
         int j = 0; while (ch.dir1[j] != tp.dir[0]) ++j;
         T.tap_ch[i] = 1 + j;
-      } else {
+      } else if (tp.order == 2) {
         int a = -1, b = -1;
         for (int j = 0; j < ch.n1; ++j) { if (ch.dir1[j] == tp.dir[0]) a = j; if (ch.dir1[j] == tp.dir[1]) b = j; }
         if (a > b) std::swap(a, b);
         int s = 0; while (!(ch.s_a[s] == a && ch.s_b[s] == b)) ++s;
         T.tap_ch[i] = 1 + ch.n1 + s;
+      } else {
+        int a = 0; while (ch.dir1[a] != tp.dir[0]) ++a;
+        int q = 0; while (ch.t_a[q] != a) ++q;
+        T.tap_ch[i] = 1 + ch.n1 + ch.n2 + q;
       }
     }
     // program
@@ -451,6 +478,11 @@ static int lower_problem(const pinn_problem_desc* d, pinn_engine* e) {
 
   // ---- tcgen05 path: supported-shape check and shared-memory plan -----------------------------------
   if (d->dtype != PINN_F32) return fail("pinn_create: the tcgen05 modes compute in bf16/fp32 and need dtype PINN_F32");
+  for (int t = 0; t < d->n_terms; ++t)
+    for (int s2 = 0; s2 < P.terms[t].n_used; ++s2)
+      if (P.terms[t].chan[s2].n3 > 0)
+        return fail("pinn_create(tc): term %d takes a third derivative; the tcgen05 path propagates derivatives up to order 2 "
+                    "(use PINN_MODE_FFMA)", t);
   e->tc_split = d->mode == PINN_MODE_TC_SPLIT ? 1 : 0;
   e->tile_pts = kTcPts;
   int tl_max = 0;
@@ -688,6 +720,7 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   memset(e->dyn, 0, sizeof e->dyn); memset(e->n_global_set, 0, sizeof e->n_global_set);
   memset(e->n_global, 0, sizeof e->n_global);
   memset(e->sampler_on, 0, sizeof e->sampler_on);
+  memset(e->sampler_kind, 0, sizeof e->sampler_kind);
   memset(e->peer_base, 0, sizeof e->peer_base);
   e->p2p_why[0] = 0;
   e->hprob = new DevProblem();
@@ -910,13 +943,9 @@ static void fill_tail(pinn_engine* e, TailArgs& t, const ScaleW& sw, void* out_g
   }
   t.timeout_ns = e->tail_timeout_ns;
   t.nranks = multi ? e->nranks : 1; t.rank = multi ? e->rank : 0;
-  t.terms_off = e->sym_terms_off;
+  t.recv_words = e->recv_words;
   if (multi)
-    for (int r = 0; r < e->nranks; ++r) {
-      char* b = (char*)e->peer_base[r];
-      t.peer_buf[0][r] = b; t.peer_buf[1][r] = b + e->sym_buf_bytes;
-      t.peer_flags[r] = (unsigned int*)(b + 2 * e->sym_buf_bytes);
-    }
+    for (int r = 0; r < e->nranks; ++r) t.peer_recv[r] = e->peer_base[r];
   t.sw = sw;
 }
 
@@ -1170,16 +1199,21 @@ static int draw_term(pinn_engine* e, int term, unsigned long long draw, const un
   const int dim = e->hprob->terms[term].dim;
   const long long n = e->sampler_n[term];
   if (grow(&e->own_pts[term], &e->own_pts_cap[term], (size_t)n * dim * e->es, e)) return 1;
-  CUDA_TRY(sample_uniform_launch(e->dtype, e->own_pts[term], n, dim, e->sampler_lb[term], e->sampler_ub[term],
-                                 e->sampler_seed[term] + 0x9E3779B97F4A7C15ull * (unsigned long long)(term + 1), draw, draw_dev, st));
+  const unsigned long long key = e->sampler_seed[term] + 0x9E3779B97F4A7C15ull * (unsigned long long)(term + 1);
+  if (e->sampler_kind[term] == PINN_SAMPLER_LHS)
+    CUDA_TRY(sample_lhs_launch(e->dtype, e->own_pts[term], n, dim, e->sampler_lb[term], e->sampler_ub[term], key, draw, draw_dev, st));
+  else
+    CUDA_TRY(sample_uniform_launch(e->dtype, e->own_pts[term], n, dim, e->sampler_lb[term], e->sampler_ub[term], key, draw, draw_dev, st));
   e->launches += 1;
   e->dyn[term].pts = e->own_pts[term]; e->dyn[term].qw = nullptr; e->dyn[term].n = n;
   return 0;
 }
 
-int pinn_set_sampler(pinn_handle e, int32_t term, int64_t n, const double* host_lb, const double* host_ub, uint64_t seed,
-                     void* stream) {
+int pinn_set_sampler_ex(pinn_handle e, int32_t term, int32_t kind, int64_t n, const double* host_lb, const double* host_ub,
+                        uint64_t seed, void* stream) {
   if (check_term(e, term, "pinn_set_sampler")) return 1;
+  if (kind != PINN_SAMPLER_UNIFORM && kind != PINN_SAMPLER_LHS) return fail("pinn_set_sampler: unknown sampler kind %d", kind);
+  if (n > 0x7fffffffLL) return fail("pinn_set_sampler: at most 2^31 - 1 points per term");
   if (n < 1) return fail("pinn_set_sampler: term %d needs at least one point", term);
   if (!host_lb || !host_ub) return fail("pinn_set_sampler: null bounds");
   if (e->reduction[term] == PINN_REDUCE_WSUM)
@@ -1190,10 +1224,15 @@ int pinn_set_sampler(pinn_handle e, int32_t term, int64_t n, const double* host_
     if (!(host_lb[r] <= host_ub[r])) return fail("pinn_set_sampler: term %d row %d has lb > ub", term, r);
     e->sampler_lb[term][r] = host_lb[r]; e->sampler_ub[term][r] = host_ub[r];
   }
-  e->sampler_on[term] = true; e->sampler_seed[term] = seed; e->sampler_n[term] = n;
+  e->sampler_on[term] = true; e->sampler_kind[term] = kind; e->sampler_seed[term] = seed; e->sampler_n[term] = n;
   if (draw_term(e, term, e->sampler_draw, &e->d_state->draw, (cudaStream_t)stream)) return 1;
   retile(e);
   return 0;
+}
+
+int pinn_set_sampler(pinn_handle e, int32_t term, int64_t n, const double* host_lb, const double* host_ub, uint64_t seed,
+                     void* stream) {
+  return pinn_set_sampler_ex(e, term, PINN_SAMPLER_UNIFORM, n, host_lb, host_ub, seed, stream);
 }
 
 int pinn_resample(pinn_handle e, void* stream) {
@@ -1257,8 +1296,9 @@ int pinn_comm_unique_id(void* out) {
   return 0;
 }
 
-// Map every rank's symmetric region [grad+terms buffer x 2 parities | per-slice flags] into this process so the fused
-// kernel's tail can add the peers' gradient slices straight over NVLink (tail.cuh).  Every rank runs the same two
+// Map every rank's receive region ([2 parities][nranks][n_theta words + term words] slots of {32-bit word, step flag})
+// into this process so the fused kernel's tail can push its reduced gradient slices straight into the peers' memory over
+// NVLink and add what the peers pushed (tail.cuh).  Every rank runs the same two
 // collectives (handle allgather, agreement allreduce) whatever its local outcome; on any failure all ranks fall back to
 // ncclAllReduce together and p2p_why says why.
 struct PeerRec {
@@ -1278,11 +1318,8 @@ static int setup_p2p(pinn_engine* e) {
   if (!e->tail_on) why("PINN_B200_TAIL=0");
   if (e->nranks > kMaxRanks) why("more ranks than one NVSwitch domain (8)");
   if (e->num_sms > kTailSlots) why("more SMs than tail slots");
-  const size_t gb = (((size_t)e->n_theta * e->es) + 255) & ~size_t(255);
-  e->sym_terms_off = (long long)gb;
-  e->sym_buf_bytes = (gb + PINN_MAX_TERMS * sizeof(double) + 255) & ~size_t(255);
-  const size_t flag_bytes = (size_t)kMaxRanks * kTailSlots * sizeof(unsigned int);
-  const size_t total = 2 * e->sym_buf_bytes + flag_bytes;
+  e->recv_words = e->n_theta * (long long)(e->es / 4) + 2 * PINN_MAX_TERMS;
+  const size_t total = (size_t)2 * (size_t)e->nranks * (size_t)e->recv_words * 8;
   PeerRec mine;
   memset(&mine, 0, sizeof mine);
   if (ok) {

@@ -6,10 +6,11 @@
 //                          self-resetting generation barrier in global memory, so CUDA-graph replays need no host state
 //   2. slice reduction     CTA b sums gradient entries [b*S, (b+1)*S) over the per-CTA partials in a FIXED order
 //                          (bitwise reproducible for a given grid); CTA 0 turns the per-CTA term sums into losses
-//   3. one-shot allreduce  (nranks > 1) the slice goes to this rank's symmetric buffer; per-slice flags are written
-//                          straight into every peer's memory over NVLink (st.release.sys), each CTA waits for the
-//                          same slice of every peer and adds the peers' slices in rank order (ld.relaxed.sys over
-//                          NVLink) -- one hop, no extra launch, identical bits on every rank
+//   3. one-shot allreduce  (nranks > 1) every reduced entry is PUSHED into each peer's receive buffer over NVLink as one
+//                          8-byte store {32 data bits, step flag} (the word and its flag arrive together: no fence, no
+//                          separate flag, no read round trip); the CTA that owns the same slice on the peer polls its
+//                          local slots until the flag carries this step, and adds the N values in rank order --
+//                          one NVLink hop, no extra launch, identical bits on every rank
 //   4. consume             write the gradient, or apply Adam in place (theta, m, v resident on the device; bias
 //                          correction from a device-side step counter, so a captured graph can be replayed)
 #pragma once
@@ -40,32 +41,13 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// one receive slot = {32 data bits, step flag}: a single aligned 8-byte access, so the word never arrives without its flag
+__device__ __forceinline__ void st_slot(uint2* p, unsigned int bits, unsigned int flag) {
+  asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(bits), "r"(flag) : "memory");
 }
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
-  float v;
-  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ float4 ld_relaxed_sys_v(const float4* p) {
-  float4 v;
-  asm volatile("ld.relaxed.sys.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double2 ld_relaxed_sys_v(const double2* p) {
-  double2 v;
-  asm volatile("ld.relaxed.sys.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+__device__ __forceinline__ uint2 ld_slot(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ unsigned long long tail_now_ns() {
@@ -129,9 +111,23 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
     __threadfence();
   }
   __syncthreads();
-  const unsigned int step1 = s_step + 1u;          // flag value of this step (0 = never signalled)
+  const unsigned int step1 = s_step + 1u;          // flag value of this step (0 = never written)
   const bool multi = ta.nranks > 1;
-  real* mybuf = multi ? reinterpret_cast<real*>(ta.peer_buf[s_step & 1u][ta.rank]) : nullptr;
+  constexpr int W = (int)sizeof(real) / 4;         // 32-bit words per scalar
+  // receive slots of (parity, source rank) on rank q: recv[q] + ((parity * nranks + src) * recv_words + word), 8 bytes each
+  const size_t par_off = (size_t)(s_step & 1u) * (size_t)ta.nranks;
+  auto push = [&](long long word, unsigned int bits) {          // this rank's word -> the same slot on every rank (self included)
+#pragma unroll
+    for (int q = 0; q < kMaxRanks; ++q)
+      if (q < ta.nranks)
+        st_slot(reinterpret_cast<uint2*>(ta.peer_recv[q]) + (par_off + (size_t)ta.rank) * (size_t)ta.recv_words + word, bits, step1);
+  };
+  auto pull = [&](int src, long long word) -> unsigned int {    // poll the local slot until the source's word of THIS step is there
+    const uint2* slot = reinterpret_cast<const uint2*>(ta.peer_recv[ta.rank]) + (par_off + (size_t)src) * (size_t)ta.recv_words + word;
+    uint2 v = ld_slot(slot);
+    if (v.y != step1) tail_spin([&] { v = ld_slot(slot); return v.y == step1; }, ta.timeout_ns);
+    return v.x;
+  };
 
   // ---- 2. term losses (CTA 0, one warp per term): L_k = scale_k * sum_b term_sums[b][k], fixed order ---------------------
   if (bid == 0) {
@@ -157,8 +153,13 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
       for (int k = 0; k < n_terms; ++k) {
         const double Lk = sL[k];
         tot += Lk * ta.sw.w[k];
-        if (multi) reinterpret_cast<double*>(reinterpret_cast<char*>(mybuf) + ta.terms_off)[k] = Lk;
-        else reinterpret_cast<real*>(ta.out_terms)[k] = real(Lk);
+        if (multi) {                                   // term losses travel as two words each behind the gradient
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(Lk);
+          push(n_theta * W + 2 * k, (unsigned int)bits);
+          push(n_theta * W + 2 * k + 1, (unsigned int)(bits >> 32));
+        } else {
+          reinterpret_cast<real*>(ta.out_terms)[k] = real(Lk);
+        }
       }
       if (!multi && ta.out_total) *reinterpret_cast<real*>(ta.out_total) = real(tot);
     }
@@ -220,47 +221,46 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
         real t = red[tid];
 #pragma unroll
         for (int k = 1; k < NG; ++k) t += red[k * EW + tid];
-        if (multi) mybuf[base + tid] = t; else consume(base + tid, t);
+        if (multi) {
+          if (W == 1) {
+            push(base + tid, (unsigned int)__float_as_uint((float)t));
+          } else {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong((double)t);
+            push(2 * (base + tid), (unsigned int)bits);
+            push(2 * (base + tid) + 1, (unsigned int)(bits >> 32));
+          }
+        } else {
+          consume(base + tid, t);
+        }
       }
       __syncthreads();
     }
   }
   if (!multi) return;
 
-  // ---- 4. one-shot allreduce over peer memory: signal slice `bid` to every peer, wait for theirs, add in rank order -------
-  // (the release store orders this CTA's slice, made visible to the signalling thread by the barrier, before the flag:
-  //  no CTA-wide system fence)
-  __syncthreads();
-  if (tid < ta.nranks && tid != ta.rank) {
-    st_release_sys(ta.peer_flags[tid] + (size_t)ta.rank * kTailSlots + bid, step1);
-    const unsigned int* mine = ta.peer_flags[ta.rank] + (size_t)tid * kTailSlots + bid;
-    tail_spin([&] { return (int)(ld_acquire_sys(mine) - step1) >= 0; }, ta.timeout_ns);
-  }
-  __syncthreads();
+  // ---- 4. receive: the same slice of every rank (own included), added in rank order -----------------------------------------
   if (want_grad) {
-    for (long long i = i0 + (long long)V * tid; i < i1; i += (long long)V * NT) {
-      real acc[V];
-#pragma unroll
-      for (int j = 0; j < V; ++j) acc[j] = real(0);
-#pragma unroll
-      for (int r = 0; r < kMaxRanks; ++r)          // all peers' 16-byte loads in flight together, added in rank order
-        if (r < ta.nranks) {
-          const vec_t v = ld_relaxed_sys_v(reinterpret_cast<const vec_t*>(reinterpret_cast<const real*>(ta.peer_buf[s_step & 1u][r]) + i));
-          const real* pv = reinterpret_cast<const real*>(&v);
-#pragma unroll
-          for (int j = 0; j < V; ++j) acc[j] += pv[j];
+    for (long long i = i0 + tid; i < i1; i += NT) {
+      real t = real(0);
+      for (int r = 0; r < ta.nranks; ++r) {
+        if (W == 1) {
+          t += (real)__uint_as_float(pull(r, i));
+        } else {
+          const unsigned long long lo = pull(r, 2 * i), hi = pull(r, 2 * i + 1);
+          t += (real)__longlong_as_double((long long)(lo | (hi << 32)));
         }
-#pragma unroll
-      for (int j = 0; j < V; ++j)
-        if (i + j < i1) consume(i + j, acc[j]);
+      }
+      consume(i, t);
     }
   }
   if (bid == 0 && tid == 0) {
     double tot = 0.0;
     for (int k = 0; k < n_terms; ++k) {
       double Lk = 0.0;
-      for (int r = 0; r < ta.nranks; ++r)
-        Lk += ld_relaxed_sys(reinterpret_cast<const double*>(reinterpret_cast<const char*>(ta.peer_buf[s_step & 1u][r]) + ta.terms_off) + k);
+      for (int r = 0; r < ta.nranks; ++r) {
+        const unsigned long long lo = pull(r, n_theta * W + 2 * k), hi = pull(r, n_theta * W + 2 * k + 1);
+        Lk += __longlong_as_double((long long)(lo | (hi << 32)));
+      }
       reinterpret_cast<real*>(ta.out_terms)[k] = real(Lk);
       tot += Lk * ta.sw.w[k];
     }

@@ -739,6 +739,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
 #endif
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------------------------
+  // pull theta (tens of KB) into L2 right away: the staging loops below then pay L2 latency, not HBM latency, per round trip
+  for (long long i = (long long)tid * 32; i < P.n_theta; i += (long long)kTcThreads * 32) tc::prefetch_l2(theta + i);
   if (tid == 0) {
     tc::mbar_init(ms.bar_mma, 1);
     tc::mbar_init(ms.bar_ld, 1);
@@ -791,30 +793,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
       fp[FP_W1 + o * 8 + k] = __ldg(&theta[w0 + i]);
     }
     for (int i = tid; i < n1w; i += kTcThreads) fp[FP_B1 + i] = __ldg(&theta[b0 + i]);
-    // thread <-> (layer, row o, chunk of 8 k): one flattened loop keeps all layers' loads in flight
-    for (int i = tid; i < (L - 2) * 64 * 8; i += kTcThreads) {
-      const int l = 1 + i / 512, r = i & 511;
-      const int o = r & 63, kc = r >> 6;
-      const int n_in = net.dims[l], n_out = net.dims[l + 1];
-      const long long woff = net.w_off[l];
-      uint8_t* thi = smem + ns.w_hi[l - 1];
-      uint8_t* tlo = smem + ns.w_lo[l - 1];
-      float w[8];
+    // thread <-> (layer, row o, chunk of 8 k).  All global loads of all layers are issued before the first conversion
+    // (fully unrolled, predicated on the layer count): one memory round trip instead of one per layer -- the step
+    // starts with theta cold in L2 when the caller's other work has evicted it
+    {
+      constexpr int kItMax = kTcMaxTL * 512 / kTcThreads;
+      const int n_items = (L - 2) * 512;
+      float w[kItMax][8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int k = kc * 8 + e;
-        w[e] = (o < n_out && k < n_in) ? __ldg(&theta[woff + o + (long long)n_out * k]) : 0.f;
+      for (int it = 0; it < kItMax; ++it) {
+        const int i = tid + it * kTcThreads;
+        if (i < n_items) {
+          const int l = 1 + i / 512, r = i & 511;
+          const int o = r & 63, kc = r >> 6;
+          const int n_in = net.dims[l], n_out = net.dims[l + 1];
+          const long long woff = net.w_off[l];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int k = kc * 8 + e;
+            w[it][e] = (o < n_out && k < n_in) ? __ldg(&theta[woff + o + (long long)n_out * k]) : 0.f;
+          }
+        }
       }
-      uint4 h, lo4;
-      h.x = tc::pack_bf16(w[0], w[1]); h.y = tc::pack_bf16(w[2], w[3]);
-      h.z = tc::pack_bf16(w[4], w[5]); h.w = tc::pack_bf16(w[6], w[7]);
-      *reinterpret_cast<uint4*>(thi + tc::swz_chunk(o, kc)) = h;
-      if (args.split) {
-        lo4.x = tc::pack_bf16(w[0] - __uint_as_float(h.x << 16), w[1] - __uint_as_float(h.x & 0xffff0000u));
-        lo4.y = tc::pack_bf16(w[2] - __uint_as_float(h.y << 16), w[3] - __uint_as_float(h.y & 0xffff0000u));
-        lo4.z = tc::pack_bf16(w[4] - __uint_as_float(h.z << 16), w[5] - __uint_as_float(h.z & 0xffff0000u));
-        lo4.w = tc::pack_bf16(w[6] - __uint_as_float(h.w << 16), w[7] - __uint_as_float(h.w & 0xffff0000u));
-        *reinterpret_cast<uint4*>(tlo + tc::swz_chunk(o, kc)) = lo4;
+#pragma unroll
+      for (int it = 0; it < kItMax; ++it) {
+        const int i = tid + it * kTcThreads;
+        if (i < n_items) {
+          const int l = 1 + i / 512, r = i & 511;
+          const int o = r & 63, kc = r >> 6;
+          uint8_t* thi = smem + ns.w_hi[l - 1];
+          uint8_t* tlo = smem + ns.w_lo[l - 1];
+          uint4 h, lo4;
+          h.x = tc::pack_bf16(w[it][0], w[it][1]); h.y = tc::pack_bf16(w[it][2], w[it][3]);
+          h.z = tc::pack_bf16(w[it][4], w[it][5]); h.w = tc::pack_bf16(w[it][6], w[it][7]);
+          *reinterpret_cast<uint4*>(thi + tc::swz_chunk(o, kc)) = h;
+          if (args.split) {
+            lo4.x = tc::pack_bf16(w[it][0] - __uint_as_float(h.x << 16), w[it][1] - __uint_as_float(h.x & 0xffff0000u));
+            lo4.y = tc::pack_bf16(w[it][2] - __uint_as_float(h.y << 16), w[it][3] - __uint_as_float(h.y & 0xffff0000u));
+            lo4.z = tc::pack_bf16(w[it][4] - __uint_as_float(h.z << 16), w[it][5] - __uint_as_float(h.z & 0xffff0000u));
+            lo4.w = tc::pack_bf16(w[it][6] - __uint_as_float(h.w << 16), w[it][7] - __uint_as_float(h.w & 0xffff0000u));
+            *reinterpret_cast<uint4*>(tlo + tc::swz_chunk(o, kc)) = lo4;
+          }
+        }
       }
     }
     for (int i = tid; i < (L - 2) * 64; i += kTcThreads) {

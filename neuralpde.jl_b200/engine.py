@@ -16,7 +16,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PINN_B200_LIB") or os.path.join(HERE, "lib", "libpinn_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_IN = 8
 MAX_TERMS = 32
 
@@ -37,7 +37,7 @@ EXPORTS = [
     "pinn_launch_count", "pinn_set_timing", "pinn_last_kernel_ms", "pinn_workspace_bytes",
     "pinn_flops_per_eval", "pinn_adam_begin", "pinn_adam_iterate", "pinn_adam_theta",
     "pinn_term_grad_stats", "pinn_term_grad_stats_host", "pinn_set_sampler", "pinn_resample", "pinn_get_points_host",
-    "pinn_comm_info",
+    "pinn_comm_info", "pinn_set_sampler_ex",
 ]
 
 
@@ -55,7 +55,7 @@ class _NetDesc(C.Structure):
 
 
 class _TapDesc(C.Structure):
-    _fields_ = [("net", C.c_int32), ("out", C.c_int32), ("order", C.c_int32), ("dir", C.c_int32 * 2)]
+    _fields_ = [("net", C.c_int32), ("out", C.c_int32), ("order", C.c_int32), ("dir", C.c_int32 * 4)]
 
 
 class _TermDesc(C.Structure):
@@ -148,6 +148,8 @@ def load_library():
     lib.pinn_loss_grad_host.restype = C.c_int
     lib.pinn_set_sampler.argtypes = [vp, i32, i64, C.POINTER(dbl), C.POINTER(dbl), C.c_uint64, vp]
     lib.pinn_set_sampler.restype = C.c_int
+    lib.pinn_set_sampler_ex.argtypes = [vp, i32, i32, i64, C.POINTER(dbl), C.POINTER(dbl), C.c_uint64, vp]
+    lib.pinn_set_sampler_ex.restype = C.c_int
     lib.pinn_resample.argtypes = [vp, vp]
     lib.pinn_resample.restype = C.c_int
     lib.pinn_get_points_host.argtypes = [vp, i32, vp]
@@ -226,8 +228,9 @@ def build_desc(spec: ProblemSpec) -> _ProblemDesc:
         taps = (_TapDesc * max(1, len(tm.taps)))()
         for i, tp in enumerate(tm.taps):
             taps[i].net, taps[i].out, taps[i].order = int(tp.net), int(tp.out), int(tp.order)
-            d = list(tp.dirs) + [0, 0]
-            taps[i].dir[0], taps[i].dir[1] = int(d[0]), int(d[1])
+            d = list(tp.dirs) + [0, 0, 0, 0]
+            for q in range(4):
+                taps[i].dir[q] = int(d[q])
         rows = (C.c_int32 * (len(spec.nets) * MAX_IN))(*([-1] * (len(spec.nets) * MAX_IN)))
         for k, n in enumerate(spec.nets):
             r = tm.net_rows[k] if tm.net_rows is not None and k < len(tm.net_rows) and tm.net_rows[k] is not None \
@@ -304,15 +307,16 @@ class Engine:
         w = None if weights is None else np.ascontiguousarray(weights, dtype=self.np_dtype)
         _check(self.lib.pinn_set_points_host(self._h, term, _ptr(flat), int(pts.shape[1]), _ptr(w), C.c_void_p(stream)))
 
-    def set_sampler(self, term: int, n: int, lb, ub, seed: int = 0, stream: int = 0):
-        """Register a device-side uniform sampler for a term (box lb..ub per point row) and draw the first sample."""
+    def set_sampler(self, term: int, n: int, lb, ub, seed: int = 0, stream: int = 0, kind: str = "uniform"):
+        """Register a device-side sampler for a term (box lb..ub per point row) and draw the first sample.
+        kind "uniform": StochasticTraining; "lhs": Latin hypercube (QuasiRandomTraining's default algorithm)."""
         lb = np.ascontiguousarray(lb, dtype=np.float64); ub = np.ascontiguousarray(ub, dtype=np.float64)
         dim = self.spec.terms[term].dim
         if lb.shape != (dim,) or ub.shape != (dim,):
             raise ValueError("term %d expects %d bounds per side, got %s / %s" % (term, dim, lb.shape, ub.shape))
-        _check(self.lib.pinn_set_sampler(self._h, int(term), int(n), lb.ctypes.data_as(C.POINTER(C.c_double)),
-                                         ub.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint64(int(seed) & (2 ** 64 - 1)),
-                                         C.c_void_p(stream)))
+        _check(self.lib.pinn_set_sampler_ex(self._h, int(term), {"uniform": 0, "lhs": 1}[kind], int(n),
+                                            lb.ctypes.data_as(C.POINTER(C.c_double)), ub.ctypes.data_as(C.POINTER(C.c_double)),
+                                            C.c_uint64(int(seed) & (2 ** 64 - 1)), C.c_void_p(stream)))
         self._n_pts = getattr(self, "_n_pts", {})
         self._n_pts[int(term)] = int(n)
 

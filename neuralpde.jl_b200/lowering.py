@@ -122,11 +122,11 @@ class _Emitter:
         dirs = tuple(sorted(dirs))
         key = (net, dirs)
         if key not in self._tap_ids:
-            if len(dirs) > 2:
+            if len(dirs) > 3 or (len(dirs) == 3 and len(set(dirs)) != 1):
                 raise LoweringError(
-                    "derivative of order %d of %s: this engine propagates exact taps up to order 2 "
-                    "(the reference's order-3/4 stencils, src/pinn_types.jl:461-474, are not covered)"
-                    % (len(dirs), depvar))
+                    "derivative of order %d of %s along %s: this engine propagates exact taps up to order 2 in any "
+                    "directions and pure third derivatives (the reference's order-4 stencil and the recursive mixed "
+                    "forms, src/pinn_types.jl:454-474, are not covered)" % (len(dirs), depvar, list(dirs)))
             self._tap_ids[key] = len(self.taps)
             self.taps.append(TapSpec(net=net, order=len(dirs), dirs=dirs))
         return self._push("tap", a=self._tap_ids[key])

@@ -551,7 +551,7 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
         if point_sets[i] is not None:
             upload(i, point_sets[i], quad_w[i])
 
-    device_sampler = isinstance(strategy, StochasticTraining) and strategy.device_sampler
+    device_sampler = isinstance(strategy, (StochasticTraining, QuasiRandomTraining)) and strategy.device_sampler
     if device_sampler:
         # the reference draws on the host and uploads every call (training_strategies.jl:277-281);
         # here each term's box is registered once and every draw is one small kernel per term
@@ -559,7 +559,8 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
             npts = strategy.points if i < n_pde else strategy.bcs_points
             lo, hi = shard_range(npts, rank, world)
             lb, ub = (np.asarray(v_, dtype=np.float64) for v_ in b)
-            eng.set_sampler(i, hi - lo, lb, ub, strategy.seed + 7919 * rank)
+            eng.set_sampler(i, hi - lo, lb, ub, strategy.seed + 7919 * rank,
+                            kind="lhs" if isinstance(strategy, QuasiRandomTraining) else "uniform")
             if world > 1:
                 eng.set_global_count(i, npts)
 
@@ -736,7 +737,8 @@ def solve(prob: OptimizationProblem, opt: Adam, maxiters: int = 100, callback: O
     rep = prob.representation
     if device_loop:
         host_resampled = (isinstance(rep.strategy, StochasticTraining) and not rep.strategy.device_sampler) or \
-                         (isinstance(rep.strategy, QuasiRandomTraining) and rep.strategy.resampling) if rep is not None else True
+                         (isinstance(rep.strategy, QuasiRandomTraining) and rep.strategy.resampling and
+                          not rep.strategy.device_sampler) if rep is not None else True
         if host_resampled:
             raise ValueError("device_loop needs point sets that live on the device: Grid, Quadrature, non-resampled "
                              "QuasiRandom, or StochasticTraining(..., device_sampler=True)")

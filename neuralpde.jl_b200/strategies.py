@@ -50,10 +50,13 @@ class QuasiRandomTraining(AbstractTrainingStrategy):
     resampling: bool = True
     minibatch: int = 0
     seed: int = 0
+    device_sampler: bool = False   # resampling on the GPU: a Latin hypercube sample per call (pinn_set_sampler_ex, kind LHS)
 
     def __post_init__(self):
         if self.bcs_points is None:
             self.bcs_points = self.points
+        if self.device_sampler and not self.resampling:
+            raise ValueError("QuasiRandomTraining(device_sampler=True) resamples on every call: it needs resampling=True")
 
 
 @dataclass

@@ -125,9 +125,16 @@ def _act_derivs(name: str, z: torch.Tensor):
 
 def exact_tap(x: torch.Tensor, theta: torch.Tensor, dims, acts, offset: int, dirs: Tuple[int, ...]) -> torch.Tensor:
     """Value (dirs=()), first (dirs=(d,)) or second (dirs=(d, e)) partial derivative of the
-    network output, propagated in closed form through every layer."""
+    network output, propagated in closed form through every layer; orders above 2 by nested autograd."""
     if len(dirs) > 2:
-        raise NotImplementedError("exact taps are implemented up to order 2")
+        # higher orders: nested reverse-mode differentiation of the network with respect to its input (independent of the
+        # closed-form propagation the engine uses); columns are independent, so summing over the batch is exact
+        xg = x.detach().clone().requires_grad_(True)
+        v = phi(xg, theta, dims, acts, offset)
+        for d_ in dirs:
+            (g,) = torch.autograd.grad(v.sum(), xg, create_graph=True)
+            v = g[d_:d_ + 1, :]
+        return v
     Ws, bs = unpack(theta, dims, offset)
     n = x.shape[1]
     h = x

@@ -49,6 +49,34 @@ def poisson1d_wide_case() -> Config:
     return Config("poisson1d_wide", sys_, [chain], GridTraining(1.0 / 299), n_pde_points=300)
 
 
+def third_order_ode_case() -> Config:
+    """1-D third-order ODE u_xxx + u u_x = cos(pi x) (the equation of reference test/NNPDE1/nnpde__pde_iii_3rd_order_ode.jl
+    written with Dxxx = Differential(x)^3 directly; stencil src/pinn_types.jl:469-474) with Dirichlet, Neumann and
+    second-derivative boundary terms; tanh / sigmoid / swish layers exercise the fourth activation derivative of the
+    reverse sweep."""
+    x = parameters("x")
+    u = variables("u")
+    Dx = Differential(x)
+    eq = Eq((Dx ** 3)(u(x)) + u(x) * Dx(u(x)), sp.cos(sp.pi * x))
+    bcs = [Eq(u(0.0), 0.0), Eq(u(1.0), -1.0), Eq(Dx(u(1.0)), 1.0), Eq((Dx ** 2)(u(0.0)), 0.25)]
+    sys_ = PDESystem(eq, bcs, [In(x, 0.0, 1.0)], [x], [u(x)])
+    chain = Chain(Dense(1, 16, "tanh"), Dense(16, 16, "sigmoid"), Dense(16, 16, "swish"), Dense(16, 1))
+    return Config("third_order_ode", sys_, [chain], GridTraining(1.0 / 49), n_pde_points=50)
+
+
+def third_order_2d_case() -> Config:
+    """u_yyy + u_xx + u_x u_y = sin(x) y on [0,1]^2: a pure third derivative along the SECOND input next to a second
+    derivative along the first (channel ordering), sin / softplus layers."""
+    x, y = parameters("x y")
+    u = variables("u")
+    Dx, Dy = Differential(x), Differential(y)
+    eq = Eq((Dy ** 3)(u(x, y)) + (Dx ** 2)(u(x, y)) + Dx(u(x, y)) * Dy(u(x, y)), sp.sin(x) * y)
+    bcs = [Eq(u(0, y), y), Eq((Dy ** 2)(u(x, 0)), x), Eq(Dy(u(x, 1)), 0.5)]
+    sys_ = PDESystem(eq, bcs, [In(x, 0.0, 1.0), In(y, 0.0, 1.0)], [x, y], [u(x, y)])
+    chain = Chain(Dense(2, 16, "sin"), Dense(16, 16, "softplus"), Dense(16, 1))
+    return Config("third_order_2d", sys_, [chain], GridTraining(0.1), n_pde_points=121)
+
+
 CASES = {
     "cfg1": lambda: configs.config1(),
     "cfg2_small": lambda: configs.config2(n=24, width=16, hidden=2),
@@ -60,6 +88,8 @@ CASES = {
     "cfg5_wide": lambda: configs.config5(points=500, bcs_points=70, n_obs=90, width=128, hidden=3),
     "mixed": mixed_derivative_case,
     "neumann_sin": neumann_sin_case,
+    "third_order_ode": third_order_ode_case,
+    "third_order_2d": third_order_2d_case,
 }
 
 

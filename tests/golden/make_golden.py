@@ -20,7 +20,10 @@ from helpers import oracle_eval              # noqa: E402
 
 
 def main():
+    only = sys.argv[1:]          # optional: regenerate only the named cases
     for name, make in CASES.items():
+        if only and name not in only:
+            continue
         cfg = make()
         theta = cfg.init_params(np.float64, seed=1)
         sets, qw, qs = point_sets(cfg)

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert set(declared) == set(npde.EXPORTS), (declared, npde.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pinn_abi_version() == 1
+    assert lib.pinn_abi_version() == 2
 
 
 def test_library_is_in_tree_and_sm100a():

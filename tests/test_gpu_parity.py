@@ -107,3 +107,28 @@ def test_term_grad_stats_and_gradient_scale_adaptive_loss():
     rep_b = npde.symbolic_discretize(cfg.pde_system, disc_b)
     tot_b, g_b = rep_b.loss_functions.full_loss_gradient(th)          # iteration 1 is already a reweighting iteration
     assert abs(tot_b - total2) <= 1e-10 * abs(total2) and rel(g_b, g_expected) < 1e-12
+
+
+def test_theta_layout_hand_computed_network_on_the_engine():
+    """The engine reads theta in the reference's ComponentArray order (weight out x in column-major, then bias, layer by
+    layer): phi of a hand-computed 2 -> 2 -> 1 network, and d(loss)/d(theta) entry by entry against central differences
+    of the hand formula (tests/test_oracle_pinning.py holds the same network for the oracle)."""
+    from test_oracle_pinning import HAND_THETA, hand_phi
+    chain = npde.Chain(npde.Dense(2, 2, "tanh"), npde.Dense(2, 1))
+    phi = npde.Phi(chain, 0, HAND_THETA.size, np.float64)
+    pts = np.array([[0.2, -1.0, 0.7], [0.9, 0.4, -0.3]])
+    want = np.array([hand_phi(x, y) for x, y in pts.T])
+    np.testing.assert_allclose(phi(pts, HAND_THETA)[0], want, rtol=1e-13)
+    # loss = mean(abs2, u(x, y) - 0.5) over the three points, through the full discretize path
+    x, y = npde.parameters("x y")
+    u = npde.variables("u")
+    sys_ = npde.PDESystem(npde.Eq(u(x, y), 0.5), [npde.Eq(u(0, y), 0.0)], [npde.In(x, 0.0, 1.0), npde.In(y, 0.0, 1.0)], [x, y], [u(x, y)])
+    rep = npde.symbolic_discretize(sys_, npde.PhysicsInformedNN(chain, npde.GridTraining(0.5), init_params=HAND_THETA))
+    rep.set_points(0, pts)
+    _, terms, grad = rep.engine.loss_grad_host(HAND_THETA, np.array([1.0, 0.0]), True)
+    loss = lambda th: float(np.mean([(hand_phi(a, b, th) - 0.5) ** 2 for a, b in pts.T]))     # noqa: E731
+    assert abs(terms[0] - loss(HAND_THETA)) < 1e-14
+    for i in range(HAND_THETA.size):
+        e = np.zeros_like(HAND_THETA); e[i] = 1e-6
+        fd = (loss(HAND_THETA + e) - loss(HAND_THETA - e)) / 2e-6
+        assert abs(grad[i] - fd) < 1e-8, (i, grad[i], fd)

@@ -96,3 +96,35 @@ def test_fd_float32_semantics_miss_1e5():
     prob = R.Problem(cfg.pde_system, cfg.chain_specs(), derivative="fd", eltype=np.float32)
     L32, _, _ = prob.loss_and_grad(g["theta"], sets[:1], sets[1:])
     assert abs(L32 - float(g["total"])) / float(g["total"]) > 1e-5
+
+
+# ---- theta layout, fixed by hand (independent of oracle.unpack and of the engine) --------------------------------------------
+# Lux.Chain(Dense(2 => 2, tanh), Dense(2 => 1)) as a ComponentArray (reference src/discretize.jl:451-465, src/pinn_types.jl:85-90):
+#   theta = [ W1[1,1], W1[2,1], W1[1,2], W1[2,2],  b1[1], b1[2],  W2[1,1], W2[1,2],  b2[1] ]      (weight out x in, column-major; bias)
+HAND_THETA = np.array([0.3, -0.7, 0.5, 0.2, 0.1, -0.4, 1.5, -0.6, 0.25])
+
+
+def hand_phi(x, y, th=HAND_THETA):
+    w11, w21, w12, w22, b1, b2, v1, v2, c = th           # W1 = [[w11, w12], [w21, w22]]
+    h1 = np.tanh(w11 * x + w12 * y + b1)
+    h2 = np.tanh(w21 * x + w22 * y + b2)
+    return v1 * h1 + v2 * h2 + c
+
+
+def test_theta_layout_hand_computed_network():
+    """A 2 -> 2 -> 1 network evaluated from scalar formulas: a row-major weight block, bias-before-weight or a transposed
+    input convention would all change the value (the four W1 entries are distinct and the inputs differ)."""
+    pts = np.array([[0.2, -1.0, 0.7], [0.9, 0.4, -0.3]])
+    want = np.array([hand_phi(x, y) for x, y in pts.T])
+    got = R.phi(torch.tensor(pts), torch.tensor(HAND_THETA), [2, 2, 1], ["tanh", "identity"]).numpy()
+    assert got.shape == (1, 3)
+    np.testing.assert_allclose(got[0], want, rtol=1e-14)
+    # the layout is not symmetric: swapping the two off-diagonal weights (a row-major reading) gives another function
+    swapped = HAND_THETA.copy(); swapped[[1, 2]] = swapped[[2, 1]]
+    assert abs(hand_phi(0.2, 0.9, swapped) - want[0]) > 1e-2
+    # first derivative tap from the hand formula: d/dx = v1 (1 - h1^2) w11 + v2 (1 - h2^2) w21
+    w11, w21, w12, w22, b1, b2, v1, v2, c = HAND_THETA
+    x, y = pts[:, 0]
+    h1, h2 = np.tanh(w11 * x + w12 * y + b1), np.tanh(w21 * x + w22 * y + b2)
+    tap = R.exact_tap(torch.tensor(pts[:, :1]), torch.tensor(HAND_THETA), [2, 2, 1], ["tanh", "identity"], 0, (0,))
+    assert abs(float(tap) - (v1 * (1 - h1 ** 2) * w11 + v2 * (1 - h2 ** 2) * w21)) < 1e-14
