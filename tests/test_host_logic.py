@@ -108,9 +108,14 @@ def test_error_behaviour_matches_reference():
     u = npde.variables("u")
     D3 = npde.Differential(x) ** 3
     vi = npde.get_vars([x, y], [u(x, y)])
-    # order-3 derivative: reference has a stencil (src/pinn_types.jl:469-474); the engine refuses loudly
+    # pure third derivatives lower to one tap (reference stencil src/pinn_types.jl:469-474) ...
+    lt = npde.lower_equation(npde.Eq(D3(u(x, y)), 0), vi)
+    assert [(t.order, tuple(t.dirs)) for t in lt.taps] == [(3, (0, 0, 0))]
+    # ... mixed third derivatives and order 4 (:461-468, and the recursive form :454-460) are refused loudly
     with pytest.raises(npde.LoweringError, match="order 3"):
-        npde.lower_equation(npde.Eq(D3(u(x, y)), 0), vi)
+        npde.lower_equation(npde.Eq(npde.Differential(y)(npde.Differential(x)(npde.Differential(x)(u(x, y)))), 0), vi)
+    with pytest.raises(npde.LoweringError, match="order 4"):
+        npde.lower_equation(npde.Eq((npde.Differential(x) ** 4)(u(x, y)), 0), vi)
     # trivial bc 0 ~ 0 (reference: ArgumentError for sampling strategies,
     # test/direct_function__trivial_bc_0_0_fails_for_some_training_strategies.jl:41-45)
     with pytest.raises(npde.LoweringError, match="no dependent variable"):
