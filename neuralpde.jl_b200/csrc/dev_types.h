@@ -104,6 +104,7 @@ struct TailArgs {
   int bump_draw;                   // advance state->draw (device-side samplers present)
   int nranks, rank;
   long long recv_words;            // 8-byte slots per (parity, source rank) block: n_theta words + 2 per term loss
+  long long* dbg;                  // -DPINN_DEBUG builds: 4 globaltimer marks per CTA (tail entry, barrier, pushed, done)
   void* peer_recv[kMaxRanks];      // receive region of every rank (peer-mapped): [2 parities][nranks][recv_words] slots
   ScaleW sw;
 };

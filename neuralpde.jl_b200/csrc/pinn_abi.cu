@@ -114,6 +114,7 @@ struct pinn_engine {
   TcNetSmem tc_nets[PINN_MAX_NETS];
   long long tc_stash_per_cta = 0;
   long long* tc_dbg = nullptr;   // device buffer for pinn_debug_tc_timeline
+  long long* tail_dbg = nullptr; // device buffer for pinn_debug_tail_marks (PINN_DEBUG builds)
   // wide tensor path (128-wide layers): streamed weights, fp32 pre-activation stash
   bool tw = false;
   int tw_off_P = 0, tw_off_S = 0, tw_off_misc = 0, tw_off_ones = 0, tw_off_nets = 0, tw_off_fp[PINN_MAX_NETS], tw_wimg[PINN_MAX_NETS];
@@ -142,6 +143,7 @@ struct pinn_engine {
   void* h_pin_in = nullptr;      // pinned theta
   void* h_pin_out = nullptr;     // pinned grad + losses
   cudaStream_t own_stream = nullptr;
+  bool zero_copy_out = false;    // h_pin_out is addressable from the device (kernel tail writes results to the host directly)
   // device-resident Adam state
   void* adam_m = nullptr;
   void* adam_v = nullptr;
@@ -764,7 +766,13 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   TRY_OR_DESTROY(dev_alloc(&e->d_grad, (size_t)e->n_theta * e->es, e));
   TRY_OR_DESTROY(dev_alloc(&e->d_out, (PINN_MAX_TERMS + 1) * e->es, e));
   err = cudaMallocHost(&e->h_pin_in, (size_t)e->n_theta * e->es);
-  if (err == cudaSuccess) err = cudaMallocHost(&e->h_pin_out, ((size_t)e->n_theta + PINN_MAX_TERMS + 1) * e->es);
+  if (err == cudaSuccess) err = cudaHostAlloc(&e->h_pin_out, ((size_t)e->n_theta + PINN_MAX_TERMS + 1) * e->es, cudaHostAllocMapped);
+  if (err == cudaSuccess) {
+    void* dptr = nullptr;
+    const char* zc = getenv("PINN_B200_ZERO_COPY");
+    e->zero_copy_out = !(zc && zc[0] == '0') && cudaHostGetDevicePointer(&dptr, e->h_pin_out, 0) == cudaSuccess && dptr == e->h_pin_out;
+    cudaGetLastError();
+  }
   // a BLOCKING stream: the *_host entry points run here and must order after uploads / sampler draws that callers
   // enqueue on the legacy default stream (pinn_set_points_host, pinn_set_sampler, pinn_resample with stream = 0)
   if (err == cudaSuccess) err = cudaStreamCreate(&e->own_stream);
@@ -944,6 +952,9 @@ static void fill_tail(pinn_engine* e, TailArgs& t, const ScaleW& sw, void* out_g
   t.timeout_ns = e->tail_timeout_ns;
   t.nranks = multi ? e->nranks : 1; t.rank = multi ? e->rank : 0;
   t.recv_words = e->recv_words;
+#ifdef PINN_DEBUG
+  t.dbg = e->tail_dbg;
+#endif
   if (multi)
     for (int r = 0; r < e->nranks; ++r) t.peer_recv[r] = e->peer_base[r];
   t.sw = sw;
@@ -1042,13 +1053,21 @@ int pinn_loss_grad_host(pinn_handle e, const void* host_theta, const double* hos
   const size_t tb = (size_t)e->n_theta * e->es;
   memcpy(e->h_pin_in, host_theta, tb);
   CUDA_TRY(cudaMemcpyAsync(e->d_theta, e->h_pin_in, tb, cudaMemcpyHostToDevice, st));
-  char* dout = (char*)e->d_out;
-  if (pinn_loss_grad(e, e->d_theta, host_weights, host_grad ? e->d_grad : nullptr, dout,
-                     dout + (size_t)e->n_terms * e->es, st))
-    return 1;
   char* hout = (char*)e->h_pin_out;
-  if (host_grad) CUDA_TRY(cudaMemcpyAsync(hout, e->d_grad, tb, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(cudaMemcpyAsync(hout + tb, e->d_out, ((size_t)e->n_terms + 1) * e->es, cudaMemcpyDeviceToHost, st));
+  if (e->zero_copy_out && e->tail_on && (e->nranks <= 1 || e->p2p)) {
+    // the kernel tail writes the gradient and the losses straight into the pinned host buffer (mapped into the device
+    // address space): no device-to-host copies after the launch, just the stream synchronisation
+    if (pinn_loss_grad(e, e->d_theta, host_weights, host_grad ? (void*)hout : nullptr, hout + tb,
+                       hout + tb + (size_t)e->n_terms * e->es, st))
+      return 1;
+  } else {
+    char* dout = (char*)e->d_out;
+    if (pinn_loss_grad(e, e->d_theta, host_weights, host_grad ? e->d_grad : nullptr, dout,
+                       dout + (size_t)e->n_terms * e->es, st))
+      return 1;
+    if (host_grad) CUDA_TRY(cudaMemcpyAsync(hout, e->d_grad, tb, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(hout + tb, e->d_out, ((size_t)e->n_terms + 1) * e->es, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));
   if (host_grad) memcpy(host_grad, hout, tb);
   if (host_term_losses) memcpy(host_term_losses, hout + tb, (size_t)e->n_terms * e->es);
@@ -1415,6 +1434,24 @@ int pinn_debug_tc_timeline(pinn_handle e, long long* host_out) {
   if (host_out) {
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(host_out, e->tc_dbg, 2000 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+#endif
+
+#ifdef PINN_DEBUG
+// diagnostic: enable (host_out == NULL) / read back the tail's per-CTA globaltimer marks of the last launch:
+// kTailSlots x {tail entry, grid barrier passed, slice reduced (+ pushed), peers' slices added}
+extern "C" int pinn_debug_tail_marks(pinn_handle e, long long* host_out) {
+  if (!e) return fail("pinn_debug_tail_marks: null handle");
+  CUDA_TRY(cudaSetDevice(e->device));
+  if (!e->tail_dbg) {
+    CUDA_TRY(cudaMalloc((void**)&e->tail_dbg, kTailSlots * 4 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(e->tail_dbg, 0, kTailSlots * 4 * sizeof(long long)));
+  }
+  if (host_out) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(host_out, e->tail_dbg, kTailSlots * 4 * sizeof(long long), cudaMemcpyDeviceToHost));
   }
   return 0;
 }

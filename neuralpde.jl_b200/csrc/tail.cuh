@@ -50,6 +50,14 @@ __device__ __forceinline__ uint2 ld_slot(const uint2* p) {
   asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int atom_add_acq_rel_gpu(unsigned int* p, unsigned int v) {
+  unsigned int old;
+  asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ void red_add_release_gpu(unsigned int* p, unsigned int v) {
+  asm volatile("red.add.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned long long tail_now_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -89,28 +97,34 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
   TailState* st = ta.state;
   const int tid = threadIdx.x, nb = gridDim.x, bid = blockIdx.x;
 
+#ifdef PINN_DEBUG
+#define TAIL_MARK(k) do { if (ta.dbg && tid == 0) ta.dbg[(size_t)bid * 4 + (k)] = (long long)tail_now_ns(); } while (0)
+#else
+#define TAIL_MARK(k) do { } while (0)
+#endif
   // ---- 1. grid barrier ----------------------------------------------------------------------------------------------
   __syncthreads();
+  TAIL_MARK(0);
   if (tid == 0) {
     const unsigned int step = *reinterpret_cast<volatile unsigned int*>(&st->step);
     const unsigned long long t_adam = *reinterpret_cast<volatile unsigned long long*>(&st->adam_t) + 1ull;
     const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(&st->gen);
     s_step = step;
     s_t = t_adam;
-    __threadfence();
-    if (atomicAdd(&st->count, 1u) == (unsigned int)(nb - 1)) {
+    // arrive with acq_rel (orders this CTA's partials, made visible to this thread by the barrier above, before the
+    // count; the last arriver acquires everyone's), release the generation: no separate fences on the critical path
+    if (atom_add_acq_rel_gpu(&st->count, 1u) == (unsigned int)(nb - 1)) {
       st->count = 0u;
       st->step = step + 1u;
       if (ta.adam_theta && want_grad) st->adam_t = t_adam;
       if (ta.bump_draw) st->draw = st->draw + 1ull;
-      __threadfence();
-      atomicAdd(&st->gen, 1u);
+      red_add_release_gpu(&st->gen, 1u);
     } else {
       tail_spin([&] { return ld_acquire_gpu(&st->gen) != gen; }, ta.timeout_ns);
     }
-    __threadfence();
   }
   __syncthreads();
+  TAIL_MARK(1);
   const unsigned int step1 = s_step + 1u;          // flag value of this step (0 = never written)
   const bool multi = ta.nranks > 1;
   constexpr int W = (int)sizeof(real) / 4;         // 32-bit words per scalar
@@ -129,8 +143,11 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
     return v.x;
   };
 
-  // ---- 2. term losses (CTA 0, one warp per term): L_k = scale_k * sum_b term_sums[b][k], fixed order ---------------------
-  if (bid == 0) {
+  // ---- 2. term losses (one warp per term): L_k = scale_k * sum_b term_sums[b][k], fixed order.  The LAST CTA does this and
+  // takes no gradient slice (when there is more than one CTA), so the term path runs beside the slice path, not in front of it
+  const int term_cta = nb - 1;
+  const int nbs = nb > 1 ? nb - 1 : 1;              // CTAs that own gradient slices
+  if (bid == term_cta) {
     double* sL = reinterpret_cast<double*>(red);          // n_terms doubles (<= 32 * 8 bytes: fits NT scalars)
     const int warp = tid >> 5, lane = tid & 31;
     for (int k = warp; k < n_terms; k += NT / 32) {
@@ -194,9 +211,10 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
   // ---- 3. slice reduction over the per-CTA partials ----------------------------------------------------------------------
   // warp g adds rows g, g + NG, ... of a 32-vector-wide window (16-byte L2 loads, all in flight at once), the NG row
   // groups are then combined through shared memory in group order: a fixed summation order for a given grid
-  long long S = (n_theta + nb - 1) / nb;
+  long long S = (n_theta + nbs - 1) / nbs;
   S = (S + V - 1) / V * V;
-  const long long i0 = (long long)bid * S;
+  const bool slice_cta = bid < nbs;
+  const long long i0 = slice_cta ? (long long)bid * S : n_theta;
   const long long i1 = (i0 + S < n_theta) ? i0 + S : n_theta;
   const int lane = tid & 31, g = tid >> 5;
   if (want_grad) {
@@ -236,36 +254,63 @@ __device__ __noinline__ void fused_tail(const TailArgs& ta, const real* partial,
       __syncthreads();
     }
   }
+  TAIL_MARK(2);
   if (!multi) return;
 
   // ---- 4. receive: the same slice of every rank (own included), added in rank order -----------------------------------------
+  // every poll is an L2 round trip: the slots of all ranks are read TOGETHER first, only the ones whose flag is not there
+  // yet are polled again (reading them one after the other cost ~0.5 us per rank and word on the critical path)
+  auto slot_of = [&](int src, long long word) {
+    return reinterpret_cast<const uint2*>(ta.peer_recv[ta.rank]) + (par_off + (size_t)src) * (size_t)ta.recv_words + word;
+  };
   if (want_grad) {
     for (long long i = i0 + tid; i < i1; i += NT) {
-      real t = real(0);
-      for (int r = 0; r < ta.nranks; ++r) {
-        if (W == 1) {
-          t += (real)__uint_as_float(pull(r, i));
-        } else {
-          const unsigned long long lo = pull(r, 2 * i), hi = pull(r, 2 * i + 1);
-          t += (real)__longlong_as_double((long long)(lo | (hi << 32)));
+      uint2 v[kMaxRanks][W];
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < ta.nranks) {
+#pragma unroll
+          for (int w = 0; w < W; ++w) v[r][w] = ld_slot(slot_of(r, W * i + w));
         }
-      }
+      real t = real(0);
+#pragma unroll
+      for (int r = 0; r < kMaxRanks; ++r)
+        if (r < ta.nranks) {
+#pragma unroll
+          for (int w = 0; w < W; ++w)
+            if (v[r][w].y != step1) v[r][w].x = pull(r, W * i + w);
+          if (W == 1) t += (real)__uint_as_float(v[r][0].x);
+          else t += (real)__longlong_as_double((long long)((unsigned long long)v[r][0].x | ((unsigned long long)v[r][W - 1].x << 32)));
+        }
       consume(i, t);
     }
   }
-  if (bid == 0 && tid == 0) {
-    double tot = 0.0;
-    for (int k = 0; k < n_terms; ++k) {
-      double Lk = 0.0;
-      for (int r = 0; r < ta.nranks; ++r) {
-        const unsigned long long lo = pull(r, n_theta * W + 2 * k), hi = pull(r, n_theta * W + 2 * k + 1);
-        Lk += __longlong_as_double((long long)(lo | (hi << 32)));
-      }
-      reinterpret_cast<real*>(ta.out_terms)[k] = real(Lk);
-      tot += Lk * ta.sw.w[k];
+  if (bid == term_cta) {
+    // term losses: one thread per (term, rank, word), then thread 0 adds them in rank order
+    unsigned int* sw = reinterpret_cast<unsigned int*>(red);           // n_terms * nranks * 2 words <= 512 <= NT * V
+    const int n_words = n_terms * ta.nranks * 2;
+    __syncthreads();
+    for (int j = tid; j < n_words; j += NT) {
+      const int k = j / (ta.nranks * 2), r = (j / 2) % ta.nranks, w = j & 1;
+      sw[j] = pull(r, n_theta * W + 2 * k + w);
     }
-    if (ta.out_total) *reinterpret_cast<real*>(ta.out_total) = real(tot);
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int k = 0; k < n_terms; ++k) {
+        double Lk = 0.0;
+        for (int r = 0; r < ta.nranks; ++r) {
+          const unsigned long long lo = sw[(k * ta.nranks + r) * 2], hi = sw[(k * ta.nranks + r) * 2 + 1];
+          Lk += __longlong_as_double((long long)(lo | (hi << 32)));
+        }
+        reinterpret_cast<real*>(ta.out_terms)[k] = real(Lk);
+        tot += Lk * ta.sw.w[k];
+      }
+      if (ta.out_total) *reinterpret_cast<real*>(ta.out_total) = real(tot);
+    }
   }
+  __syncthreads();
+  TAIL_MARK(3);
 }
 
 }  // namespace pinn

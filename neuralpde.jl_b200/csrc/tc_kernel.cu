@@ -24,6 +24,10 @@
 #include "tc_common.cuh"
 #include "tail.cuh"
 
+#ifndef PINN_TC_PREFETCH
+#define PINN_TC_PREFETCH 0      // 1: software-pipelined TMEM loads in the tensor-layer epilogues (measurement variant)
+#endif
+
 namespace pinn {
 
 // CTA-wide constants kept in shared memory so the per-network passes (separate functions) do not
@@ -119,12 +123,30 @@ __device__ __forceinline__ void tl_fwd_loop(const LoopCtx lc, const Chan<N1, N2>
   float u[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) u[c] = up[c];
+#if PINN_TC_PREFETCH
+  // software pipeline: the TMEM loads of granule g + 1 are in flight while granule g is evaluated
+  float zn[C][GW];
+#pragma unroll
+  for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + lc.g0 * GW, zn[c]);
+#endif
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
     float z[C][GW];
+#if PINN_TC_PREFETCH
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int i = 0; i < GW; ++i) z[c][i] = zn[c][i];
+    if (g + 1 < lc.g1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + (g + 1) * GW, zn[c]);
+    }
+#else
 #pragma unroll
     for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + g * GW, z[c]);
     tc::tmem_ld_wait();
+#endif
 #pragma unroll
     for (int i = 0; i < GW; i += 2) {
       P2 zz[C], hv[C];
@@ -156,10 +178,34 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
   float ub[C];
 #pragma unroll
   for (int c = 0; c < C; ++c) ub[c] = ubp[c];
+#if PINN_TC_PREFETCH
+  float zn[C][GWB], hn[C][GWB];
+#pragma unroll
+  for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_Y + c * 32 + lc.g0 * GWB, zn[c]);
+  if (!lc.flag) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + lc.c0 + lc.g0 * GWB, hn[c]);
+  }
+#endif
 #pragma unroll 1
   for (int g = lc.g0; g < lc.g1; ++g) {
     const int ocol = lc.c0 + g * GWB;
     float z[C][GWB], hb[C][GWB];
+#if PINN_TC_PREFETCH
+    tc::tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+#pragma unroll
+      for (int i = 0; i < GWB; ++i) { z[c][i] = zn[c][i]; hb[c][i] = hn[c][i]; }
+    if (g + 1 < lc.g1) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_Y + c * 32 + (g + 1) * GWB, zn[c]);
+      if (!lc.flag) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + ocol + GWB, hn[c]);
+      }
+    }
+#else
 #pragma unroll
     for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_Y + c * 32 + g * GWB, z[c]);
     if (!lc.flag) {
@@ -167,6 +213,7 @@ __device__ __forceinline__ void tl_bwd_loop(const LoopCtx lc, const Chan<N1, N2>
       for (int c = 0; c < C; ++c) tmem_ldg(lc.taddr + TM_X + c * 64 + ocol, hb[c]);
     }
     tc::tmem_ld_wait();
+#endif
     if (lc.flag) {
 #pragma unroll
       for (int i = 0; i < GWB; ++i) {
