@@ -377,16 +377,13 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         peak = pk["bf16_tflops"] if tensor_bound else 74.0            # fp32 FMA: 148 SMs x 128 lanes x 2 x 1.965 GHz
         # DRAM traffic of the dominant kernel: measured once per round with `ncu --set full` (profiles/), not re-measured here
         traffic, traffic_src = None, None
-        for fn in ("r02_ncu_traffic.json", "r01_ncu_traffic.json"):
-            try:
-                with open(os.path.join(ROOT, "profiles", fn)) as fh:
-                    ent = json.load(fh).get("%s_%s_n%d" % (args.config, mode, args.n)) or \
-                        (json.load(open(os.path.join(ROOT, "profiles", fn))).get("%s_n%d" % (mode, args.n)) if args.config == "cfg2" else None)
-                if ent and world == 1:
-                    traffic, traffic_src = int(ent["dram_bytes_read"]) + int(ent["dram_bytes_write"]), ent["source"]
-                    break
-            except (OSError, ValueError, KeyError):
-                pass
+        try:
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as fh:
+                ent = json.load(fh).get("%s_%s_n%d" % (args.config, mode, args.n))
+            if ent and world == 1:
+                traffic, traffic_src = int(ent["dram_bytes_read"]) + int(ent["dram_bytes_write"]), ent["source"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True,

@@ -917,6 +917,8 @@ static int launch_fused(pinn_engine* e, const FfmaArgs& a, int grid, cudaStream_
   t.tile_begin = a.tile_begin; t.tile_end = a.tile_end; t.mode = a.mode; t.resid_out = (float*)a.resid_out;
   t.off_P = e->tc_off_P; t.off_Q = e->tc_off_Q; t.off_misc = e->tc_off_misc; t.off_ones = e->tc_off_ones; t.mx_dim = e->tc_mx_dim; t.mx_taps = e->tc_mx_taps;
   t.dbg = e->tc_dbg;
+  t.n_nets = e->hprob->n_nets; t.n_terms = e->n_terms; t.n_theta = e->n_theta;
+  for (int k = 0; k < e->n_terms; ++k) t.term_dim[k] = (unsigned char)e->hprob->terms[k].dim;
   t.off_Q_bytes = e->tc_off_Q - e->tc_off_P;   // P and Q regions have the same size
   for (int k = 0; k < PINN_MAX_NETS; ++k) {
     t.nets[k] = e->tc_nets[k];

@@ -786,8 +786,28 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
 #endif
 
   // ---- per-CTA setup --------------------------------------------------------------------------------------------------------
-  // pull theta (tens of KB) into L2 right away: the staging loops below then pay L2 latency, not HBM latency, per round trip
-  for (long long i = (long long)tid * 32; i < P.n_theta; i += (long long)kTcThreads * 32) tc::prefetch_l2(theta + i);
+  // The step usually starts with everything cold in L2 (the caller's other work evicted it).  Pull what the serial setup
+  // code is about to read -- theta (tens of KB), the network / term descriptors and this CTA's first point tile -- into L2
+  // right away, from counts that travel in the launch arguments: the dependent loads below then pay L2 latency, not a chain
+  // of HBM round trips.
+  for (long long i = (long long)tid * 32; i < args.n_theta; i += (long long)kTcThreads * 32) tc::prefetch_l2(theta + i);
+  {
+    const char* nets0 = reinterpret_cast<const char*>(&Pp->nets[0]);
+    const char* terms0 = reinterpret_cast<const char*>(&Pp->terms[0]);
+    const int nb_nets = args.n_nets * (int)sizeof(DevNet), nb_terms = args.n_terms * (int)sizeof(DevTerm);
+    if (tid == 0) tc::prefetch_l2(Pp);
+    for (int o = tid * 128; o < nb_nets; o += kTcThreads * 128) tc::prefetch_l2(nets0 + o);
+    for (int o = tid * 128; o < nb_terms; o += kTcThreads * 128) tc::prefetch_l2(terms0 + o);
+    const int tile = args.tile_begin + (int)blockIdx.x;
+    if (tile < args.tile_end && tid < 32) {
+      int ti = 0;
+      while (ti + 1 < args.n_terms && tile >= args.dyn[ti + 1].tile0) ++ti;
+      const long long p0 = (long long)(tile - args.dyn[ti].tile0) * kTcPts;
+      const long long row_bytes = 4ll * args.term_dim[ti];
+      const long long off = p0 * row_bytes + (long long)tid * 128;
+      if (off < args.dyn[ti].n * row_bytes) tc::prefetch_l2(reinterpret_cast<const char*>(args.dyn[ti].pts) + off);
+    }
+  }
   if (tid == 0) {
     tc::mbar_init(ms.bar_mma, 1);
     tc::mbar_init(ms.bar_ld, 1);

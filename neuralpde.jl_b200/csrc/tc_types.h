@@ -50,6 +50,9 @@ struct TcArgs {
   int off_Q_bytes;              // size of the Q tile region
   int off_ones;                 // 1 KB constant atom: bf16 1.0 in column 0 of 8 swizzled rows (bias gradient by MMA)
   int mx_dim, mx_taps;          // sizes of the per-tile coordinate / tap arrays in the misc region
+  int n_nets, n_terms;          // copies of the descriptor's counts (so the kernel can prefetch it before its first read)
+  long long n_theta;
+  unsigned char term_dim[PINN_MAX_TERMS];   // rows per point of every term (first-tile prefetch)
   TcNetSmem nets[PINN_MAX_NETS];
   int net_ak[PINN_MAX_NETS];   // 1: every hidden activation is tanh (fast path), 0: generic
   double seed[PINN_MAX_TERMS];
