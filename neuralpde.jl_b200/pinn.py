@@ -320,6 +320,20 @@ class PhysicsInformedNN(AbstractPINN):
             self.self_increment = False
 
 
+class BayesianPINN(AbstractPINN):
+    """``BayesianPINN(args...; dataset = nothing, kwargs...)`` (reference src/pinn_types.jl:214-245): wraps a
+    PhysicsInformedNN; ``symbolic_discretize`` then builds ``full_loss_function(θ, allstd)`` = the weighted
+    log-likelihood (src/discretize.jl:653-757) that the HMC samplers of ext/bpinn consume.  The sampler itself is out of
+    scope; the likelihood and its θ-gradient come from the same fused kernel."""
+
+    def __init__(self, *args, dataset=None, **kwargs):
+        self.pinn = PhysicsInformedNN(*args, **kwargs)
+        self.dataset = (None, None) if dataset is None else tuple(dataset)
+
+    def __getattr__(self, name):                  # Base.getproperty forwarding (:236-240)
+        return getattr(self.pinn, name)
+
+
 @dataclass
 class PINNLossFunctions:
     bc_loss_functions: List[Callable]
@@ -408,8 +422,19 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
                         world: int = 1) -> PINNRepresentation:
     """Build the engine problem for a PDESystem (reference src/discretize.jl:413-767).
     ``rank`` / ``world`` shard every term's point set contiguously."""
+    bayes = isinstance(discretization, BayesianPINN)
+    if bayes:
+        if any(ds is not None for ds in discretization.dataset):
+            raise ValueError("BayesianPINN: dataset points (physics loss evaluated at observation sites, "
+                             "src/training_strategies.jl:86-113) are not supported; pass observations as a DataLoss")
+        if not isinstance(discretization.pinn.strategy, GridTraining):
+            raise ValueError("BayesianPINN: the reference defines the log-likelihood form for GridTraining only "
+                             "(merge_strategy_with_loglikelihood_function, src/training_strategies.jl:50-113)")
+        if discretization.pinn.adaptive_loss is not None and not isinstance(discretization.pinn.adaptive_loss, NonAdaptiveLoss):
+            raise ValueError("BayesianPINN: adaptive loss weights are not supported with the log-likelihood form")
+        discretization = discretization.pinn
     if not isinstance(discretization, PhysicsInformedNN):
-        raise TypeError("symbolic_discretize: expected a PhysicsInformedNN")
+        raise TypeError("symbolic_discretize: expected a PhysicsInformedNN or BayesianPINN")
     d = discretization
     eqs, bcs, domains = list(pde_system.eqs), list(pde_system.bcs), list(pde_system.domain)
     if len(bcs) == 0:
@@ -691,6 +716,42 @@ def symbolic_discretize(pde_system: PDESystem, discretization: PhysicsInformedNN
         if n_global is not None:
             eng.set_global_count(i, n_global)
     rep.set_points = set_points
+    if bayes:
+        # BayesianPINN (src/discretize.jl:653-757): the objective is the weighted LOG-LIKELIHOOD of zero residuals under
+        # independent Gaussians, logpdf(MvNormal(r, sigma^2 I), 0) = -n/2 log(2 pi) - n log(sigma) - sum(r^2) / (2 sigma^2) per
+        # term (get_points_loss_functions, src/training_strategies.jl:115-128) -- the sum of squares is n * mean(abs2, r),
+        # which the fused kernel returns per term, and its theta-gradient is the engine's weighted gradient with weights
+        # -W n / (2 sigma^2).  As in the reference the per-group log-likelihoods are SUMMED before the weight vector
+        # multiplies them (:682-738): every weight of a group scales the whole group sum.
+        n_k = np.array([point_sets[i].shape[1] for i in range(n_pde + n_bc)], dtype=np.float64)
+
+        def _loglik(theta, allstd, want_grad):
+            stdpdes, stdbcs, stdextra = allstd
+            sig = np.concatenate([np.asarray(stdpdes, dtype=np.float64), np.asarray(stdbcs, dtype=np.float64)])
+            if sig.shape != (n_pde + n_bc,):
+                raise ValueError("allstd: need %d pde and %d bc standard deviations" % (n_pde, n_bc))
+            Wg = np.concatenate([np.full(n_pde, weights["pde"].sum()), np.full(n_bc, weights["bc"].sum())])
+            c = -Wg * n_k / (2.0 * sig ** 2)
+            th = np.asarray(theta, dtype=dtype)
+            has_add = isinstance(add, DataLoss)
+            if has_add:
+                _, t0, _ = eng.loss_grad_host(th, np.concatenate([c, [0.0]]), False)
+                A = float(t0[-1])                  # the additional loss VALUE is one observation of Normal(0, stdextra) (:745)
+                c_all = np.concatenate([c, [-weights["add"][0] * A / float(stdextra) ** 2]])
+            else:
+                c_all = c
+            total, terms, grad = eng.loss_grad_host(th, c_all, want_grad)
+            const = float(np.sum(Wg * (-0.5 * n_k * np.log(2.0 * np.pi) - n_k * np.log(sig))))
+            ll = const + float(np.dot(c, np.asarray(terms[:n_pde + n_bc], dtype=np.float64)))
+            if has_add:
+                s_e = float(stdextra)
+                ll += weights["add"][0] * (-np.log(s_e * np.sqrt(2.0 * np.pi)) - A * A / (2.0 * s_e ** 2))
+            if d.self_increment:
+                iteration[0] += 1
+            return ll, grad
+
+        lf.full_loss_function = lambda theta, allstd: _loglik(theta, allstd, False)[0]
+        lf.full_loss_gradient = lambda theta, allstd: _loglik(theta, allstd, True)
     return rep
 
 

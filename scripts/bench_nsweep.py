@@ -10,7 +10,7 @@ dev = torch.device("cuda")
 print("| grid | PDE points | mode | ms / step | M pts/s | TFLOP/s (algorithmic) |")
 print("|---|---|---|---|---|---|")
 for n in (128, 256, 512, 1024, 2048):
-    for mode in ("tc_split", "tc_bf16", "ffma"):
+    for mode in (sys.argv[1:] or ("tc_split", "tc_bf16", "ffma")):
         if mode == "ffma" and n > 1024: continue
         cfg = configs.config2(n=n)
         rep = npde.symbolic_discretize(cfg.pde_system, cfg.discretization(dtype=np.float32, mode=mode))

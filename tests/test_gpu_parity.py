@@ -132,3 +132,37 @@ def test_theta_layout_hand_computed_network_on_the_engine():
         e = np.zeros_like(HAND_THETA); e[i] = 1e-6
         fd = (loss(HAND_THETA + e) - loss(HAND_THETA - e)) / 2e-6
         assert abs(grad[i] - fd) < 1e-8, (i, grad[i], fd)
+
+
+def test_bayesian_pinn_loglikelihood_and_gradient():
+    """BayesianPINN's objective (reference src/discretize.jl:653-757, src/training_strategies.jl:115-128): the weighted sum
+    of logpdf(MvNormal(residual, sigma^2 I), 0) over the Grid sets, plus logpdf(Normal(0, stdextra), additional_loss).
+    Checked against the same formula evaluated with the float64 oracle's residuals (autograd for the gradient)."""
+    import torch
+    from oracle import reference as R
+    cfg = configs.config2(n=12, width=16, hidden=2)
+    rng = np.random.default_rng(2)
+    X = rng.random((2, 40))
+    data = npde.DataLoss("u", X, np.sin(np.pi * X[0]) * np.sin(np.pi * X[1]) / (2 * np.pi ** 2))
+    theta = cfg.init_params(np.float64, seed=3)
+    disc = npde.BayesianPINN(cfg.chains[0], cfg.strategy, init_params=theta, additional_loss=data)
+    rep = npde.symbolic_discretize(cfg.pde_system, disc)
+    allstd = [[0.05], [0.1, 0.2, 0.3, 0.4], 0.7]
+    ll, g = rep.loss_functions.full_loss_gradient(theta, allstd)
+    assert abs(rep.loss_functions.full_loss_function(theta, allstd) - ll) <= 1e-12 * abs(ll)
+    # oracle: residual vectors -> the reference's formula
+    sys_ = cfg.pde_system
+    prob = R.Problem(sys_, cfg.chain_specs(), derivative="exact")
+    ps, bs = R.generate_training_sets(sys_.domain, cfg.strategy.dx, sys_.eqs, sys_.bcs, sys_.ivs, sys_.dvs)
+    th = torch.tensor(theta, requires_grad=True)
+    def logpdf0(r, s):          # logpdf(MvNormal(r, s^2 I), 0)
+        n = r.numel()
+        return -0.5 * n * np.log(2 * np.pi) - n * np.log(s) - (r ** 2).sum() / (2 * s ** 2)
+    ll_pde = sum(logpdf0(prob.residual(eq, torch.as_tensor(c), th), s) for eq, c, s in zip(sys_.eqs, ps, allstd[0]))
+    ll_bc = sum(logpdf0(prob.residual(eq, torch.as_tensor(c), th), s) for eq, c, s in zip(sys_.bcs, bs, allstd[1]))
+    A = prob.data_loss(data.depvar, data.points, data.values)(th)
+    ll_add = -np.log(allstd[2] * np.sqrt(2 * np.pi)) - A ** 2 / (2 * allstd[2] ** 2)
+    want = 1.0 * ll_pde + 4.0 * ll_bc + ll_add        # unit weights: every weight of a group scales the group SUM (:732-738)
+    want.backward()
+    assert abs(ll - float(want)) <= 1e-10 * abs(float(want)), (ll, float(want))
+    assert rel(g, th.grad.numpy()) < 1e-9

@@ -266,3 +266,16 @@ def test_hoisted_and_plain_lowering_agree(name):
         r_hoist = _run_ir(hoisted.prog, hoisted.augment(X), taps)
         np.testing.assert_allclose(r_hoist, r_plain, rtol=1e-13, atol=1e-14)
         assert plain.augment(X).shape[0] == X.shape[0]                  # no extra rows without hoisting
+
+
+def test_bayesian_pinn_wraps_a_physics_informed_nn_and_validates():
+    """BayesianPINN(args...; dataset, kwargs...) forwards to PhysicsInformedNN (reference src/pinn_types.jl:231-245); the
+    log-likelihood form exists for GridTraining only (src/training_strategies.jl:50-113)."""
+    from neuralpde_jl_b200 import configs
+    cfg = configs.config2(n=8, width=8, hidden=2)
+    b = npde.BayesianPINN(cfg.chains[0], cfg.strategy, param_estim=False)
+    assert isinstance(b.pinn, npde.PhysicsInformedNN) and tuple(b.dataset) == (None, None) and b.strategy is cfg.strategy
+    with pytest.raises(ValueError, match="GridTraining only"):
+        npde.symbolic_discretize(cfg.pde_system, npde.BayesianPINN(cfg.chains[0], npde.StochasticTraining(16)))
+    with pytest.raises(ValueError, match="dataset points"):
+        npde.symbolic_discretize(cfg.pde_system, npde.BayesianPINN(cfg.chains[0], cfg.strategy, dataset=(np.zeros((3, 3)), None)))
