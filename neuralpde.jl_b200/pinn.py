@@ -813,25 +813,29 @@ def solve(prob: OptimizationProblem, opt: Adam, maxiters: int = 100, callback: O
             return np.concatenate([weights["pde"], weights["bc"]] + ([weights["add"]] if rep.additional_loss is not None else []))
 
         adaptive = not isinstance(adaloss, NonAdaptiveLoss)
+
+        def reweight(it):
+            """what full_loss_function does at iteration `it` before forming the weighted sum (src/discretize.jl:574-588):
+            theta is read back once, the term losses are evaluated and handed to the adaptive loss"""
+            th = eng.adam_theta()
+            _, terms0, _ = eng.loss_grad_host(th, term_w(), False)
+            adaloss.update(it, terms0[:n_pde], terms0[n_pde:n_pde + n_bc], weights,
+                           term_grad_stats=lambda i: eng.term_grad_stats_host(i, th))
+
+        if adaptive and (iteration[0] + 1) % adaloss.reweight_every != 0:
+            reweight(iteration[0] + 1)          # the reference's closures see every iteration: SoftAdapt / ReLoBRaLo seed here
         while done < maxiters:
             n = min(chunk, maxiters - done)
             if adaptive:
-                # iterations up to (not including) the next reweighting run on the device with the current weights; the
-                # reweighting iteration reads theta back once, evaluates the term losses, updates the weights
-                # (src/discretize.jl:574-588 order) and takes its step with the new ones
+                # iterations before the next reweighting run on the device with the current weights; the reweighting
+                # iteration itself updates the weights first and takes its step with the new ones
                 nxt = (iteration[0] // adaloss.reweight_every + 1) * adaloss.reweight_every
-                n = min(n, max(nxt - iteration[0] - 1, 0))
-                if n == 0:
-                    th = eng.adam_theta()
-                    _, terms0, _ = eng.loss_grad_host(th, term_w(), False)
-                    iteration[0] += 1
-                    adaloss.update(iteration[0], terms0[:n_pde], terms0[n_pde:n_pde + n_bc], weights,
-                                   term_grad_stats=lambda i: eng.term_grad_stats_host(i, th))
+                if nxt - iteration[0] == 1:
+                    reweight(nxt)
                     n = 1
-                    iteration[0] -= 1
-            obj, terms = eng.adam_iterate(n, term_w())
-            if adaptive and n > 0 and not hasattr(adaloss, "_seen_first"):
-                adaloss._seen_first = True
+                else:
+                    n = min(n, nxt - iteration[0] - 1)
+            obj, _ = eng.adam_iterate(n, term_w())
             done += n
             iteration[0] += n
             if callback is not None and callback({"iter": done, "u": None}, obj):

@@ -279,3 +279,47 @@ def test_bayesian_pinn_wraps_a_physics_informed_nn_and_validates():
         npde.symbolic_discretize(cfg.pde_system, npde.BayesianPINN(cfg.chains[0], npde.StochasticTraining(16)))
     with pytest.raises(ValueError, match="dataset points"):
         npde.symbolic_discretize(cfg.pde_system, npde.BayesianPINN(cfg.chains[0], cfg.strategy, dataset=(np.zeros((3, 3)), None)))
+
+
+def test_device_loop_breaks_at_reweighting_iterations():
+    """solve(device_loop=True) with an adaptive loss: the device-resident loop runs up to the iteration before each
+    reweighting, the reweighting iteration evaluates the term losses at the current theta, updates the weights and takes
+    its step with the NEW weights (order of src/discretize.jl:574-588).  Driven with a stub engine (no GPU)."""
+    from neuralpde_jl_b200.pinn import OptimizationFunction, OptimizationProblem, solve
+
+    class StubEngine:
+        def __init__(self):
+            self.log, self.steps = [], 0
+        def adam_begin(self, th, *a): self.log.append(("begin",))
+        def adam_theta(self): return np.full(3, float(self.steps))
+        def loss_grad_host(self, th, w, want_grad):
+            self.log.append(("loss", self.steps, tuple(np.round(w, 6))))
+            return 1.0, np.array([2.0 + self.steps, 1.0, 3.0]), None
+        def term_grad_stats_host(self, i, th): return (1.0, 1.0)
+        def adam_iterate(self, n, w):
+            self.log.append(("iterate", n, tuple(np.round(w, 6))))
+            self.steps += n
+            return 0.5, np.zeros(3)
+
+    class Rep:
+        pass
+    rep = Rep()
+    rep.strategy = GridTraining(0.1); rep.engine = StubEngine()
+    rep.adaloss = npde.MiniMaxAdaptiveLoss(4, pde_max_optimiser=npde.Descent(0.1), bc_max_optimiser=npde.Descent(0.5))
+    rep.weights = {"pde": np.ones(1), "bc": np.ones(2), "add": np.ones(1)}
+    rep.iteration = [0]; rep.eqs = [0]; rep.bcs = [0, 1]; rep.additional_loss = None
+    prob = OptimizationProblem(OptimizationFunction(None, None), np.zeros(3), None, rep)
+    sol = solve(prob, npde.Adam(0.01), maxiters=10, device_loop=True, chunk=50)
+    log = rep.engine.log
+    assert sol.iterations == 10 and rep.iteration[0] == 10
+    its = [e for e in log if e[0] == "iterate"]
+    # 3 iterations with unit weights, reweight at iteration 4 (theta after 3 steps), 1 step with the new weights, 3 more,
+    # reweight at 8 (theta after 7 steps), 1 step, then the remaining 2
+    assert [e[1] for e in its] == [3, 1, 3, 1, 2]
+    assert its[0][2] == (1.0, 1.0, 1.0)
+    w4 = (1.0 + 0.1 * 5.0, 1.0 + 0.5 * 1.0, 1.0 + 0.5 * 3.0)            # losses at steps = 3: [5, 1, 3]
+    assert its[1][2] == w4 and its[2][2] == w4
+    w8 = (w4[0] + 0.1 * 9.0, w4[1] + 0.5, w4[2] + 1.5)                  # losses at steps = 7: [9, 1, 3]
+    assert its[3][2] == w8 and its[4][2] == w8
+    losses = [e for e in log if e[0] == "loss"]
+    assert [e[1] for e in losses] == [0, 3, 7]                          # the seeding call + the two reweightings
