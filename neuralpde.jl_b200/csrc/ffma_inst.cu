@@ -16,7 +16,8 @@ namespace pinn {
 
 cudaError_t PINN_LAUNCH_NAME(const FfmaArgs& a, int grid, size_t smem, cudaStream_t st) {
   auto k = ffma_loss_grad_kernel<PINN_INST_REAL, (PINN_INST_BUFS != 0)>;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t granted[64] = {0};
+  cudaError_t e = ensure_dynamic_smem(k, smem, granted);
   if (e != cudaSuccess) return e;
   return launch_fused_kernel(k, a, grid, kThreads, smem, st, a.tail.state != nullptr);
 }

@@ -143,6 +143,7 @@ struct pinn_engine {
   void* h_pin_in = nullptr;      // pinned theta
   void* h_pin_out = nullptr;     // pinned grad + losses
   cudaStream_t own_stream = nullptr;
+  bool h2d_direct = false;       // PINN_B200_H2D_DIRECT=1: small theta copied from the caller's (pageable) buffer directly
   bool zero_copy_out = false;    // h_pin_out is addressable from the device (kernel tail writes results to the host directly)
   // device-resident Adam state
   void* adam_m = nullptr;
@@ -769,6 +770,8 @@ int pinn_create(const pinn_problem_desc* d, pinn_handle* out) {
   if (err == cudaSuccess) err = cudaHostAlloc(&e->h_pin_out, ((size_t)e->n_theta + PINN_MAX_TERMS + 1) * e->es, cudaHostAllocMapped);
   if (err == cudaSuccess) {
     void* dptr = nullptr;
+    const char* hd = getenv("PINN_B200_H2D_DIRECT");
+    e->h2d_direct = hd && hd[0] == '1';
     const char* zc = getenv("PINN_B200_ZERO_COPY");
     e->zero_copy_out = !(zc && zc[0] == '0') && cudaHostGetDevicePointer(&dptr, e->h_pin_out, 0) == cudaSuccess && dptr == e->h_pin_out;
     cudaGetLastError();
@@ -1053,8 +1056,14 @@ int pinn_loss_grad_host(pinn_handle e, const void* host_theta, const double* hos
   CUDA_TRY(cudaSetDevice(e->device));
   cudaStream_t st = e->own_stream;
   const size_t tb = (size_t)e->n_theta * e->es;
-  memcpy(e->h_pin_in, host_theta, tb);
-  CUDA_TRY(cudaMemcpyAsync(e->d_theta, e->h_pin_in, tb, cudaMemcpyHostToDevice, st));
+  if (e->h2d_direct && tb <= 65536) {
+    // small theta: the driver inlines a pageable copy of <= 64 KB into the command stream (and returns once it is staged),
+    // which is cheaper than staging it ourselves in pinned memory and programming a DMA
+    CUDA_TRY(cudaMemcpyAsync(e->d_theta, host_theta, tb, cudaMemcpyHostToDevice, st));
+  } else {
+    memcpy(e->h_pin_in, host_theta, tb);
+    CUDA_TRY(cudaMemcpyAsync(e->d_theta, e->h_pin_in, tb, cudaMemcpyHostToDevice, st));
+  }
   char* hout = (char*)e->h_pin_out;
   if (e->zero_copy_out && e->tail_on && (e->nranks <= 1 || e->p2p)) {
     // the kernel tail writes the gradient and the losses straight into the pinned host buffer (mapped into the device

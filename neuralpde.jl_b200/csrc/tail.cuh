@@ -22,6 +22,19 @@
 
 namespace pinn {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and size instead of on every launch (host time of the
+// per-step call path); cache: bytes already granted on device d
+template <typename K>
+static cudaError_t ensure_dynamic_smem(K kernel, size_t smem, size_t (&granted)[64]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && granted[dev] >= smem) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) granted[dev] = smem;
+  return e;
+}
+
 // launch with the cooperative attribute when the kernel ends with the grid-wide tail (all CTAs must be co-resident)
 template <typename K, typename A>
 static cudaError_t launch_fused_kernel(K kernel, const A& a, int grid, int threads, size_t smem, cudaStream_t st, bool coop) {

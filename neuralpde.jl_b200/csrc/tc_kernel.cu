@@ -1050,7 +1050,8 @@ size_t tc_misc_bytes(int mx_dim, int mx_taps) {
 }
 
 cudaError_t tc_launch(const TcArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tc_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t granted[64] = {0};
+  cudaError_t e = ensure_dynamic_smem(tc_loss_grad_kernel, smem, granted);
   if (e != cudaSuccess) return e;
   return launch_fused_kernel(tc_loss_grad_kernel, a, grid, kTcThreads, smem, st, a.tail.state != nullptr);
 }

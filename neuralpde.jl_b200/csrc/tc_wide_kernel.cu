@@ -1028,7 +1028,8 @@ cudaError_t tw_pack_launch(const TwPackArgs& a, cudaStream_t st) {
 }
 
 cudaError_t tw_launch(const TwArgs& a, int grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(tw_loss_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  static size_t granted[64] = {0};
+  cudaError_t e = ensure_dynamic_smem(tw_loss_grad_kernel, smem, granted);
   if (e != cudaSuccess) return e;
   return launch_fused_kernel(tw_loss_grad_kernel, a, grid, kTcThreads, smem, st, a.tail.state != nullptr);
 }
