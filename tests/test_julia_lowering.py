@@ -98,3 +98,26 @@ def test_constant_boundary_coordinate_becomes_an_appended_row():
     assert jl.taps == [(0, 0, ())] and jl.net_rows[0] == [0, 1, 2] and jl.const_rows == {2: 1.0} and jl.dim == 3
     X = np.random.default_rng(0).uniform(size=(3, 5))
     np.testing.assert_allclose(_run(jl.prog, X, [np.arange(5.0)], [0.0]), np.arange(5.0) - 1.0)
+
+
+def test_lowering_refuses_what_the_engine_cannot_evaluate():
+    """Loud failures, as the Julia pass raises ArgumentError: a function without an opcode, an unknown binding, a
+    derivative whose epsilon vectors are not one-hot."""
+    base = _text("cfg2_bc")
+    bad_fn = base.replace("u(cord1, θ, phi) .- 0.0", "besselj.(u(cord1, θ, phi)) .- 0.0")
+    with pytest.raises(ValueError, match="outside the grammar"):
+        lower_loss_function(parse(bad_fn), ["u"])
+    bad_bind = base.replace("(cord[[1], :], cord[[2], :])", "(cord[[1], :], somewhere(y))")
+    with pytest.raises(ValueError, match="unrecognised binding"):
+        lower_loss_function(parse(bad_bind), ["u"])
+    pde = _text("cfg2_pde").replace("[[0.0001220703125, 0.0], [0.0001220703125, 0.0]]", "[[0.0001220703125, 0.0001220703125], [0.0001220703125, 0.0]]")
+    with pytest.raises(AssertionError):
+        lower_loss_function(parse(pde), ["u"])
+
+
+def test_common_subexpressions_are_emitted_once():
+    """The IR is SSA with value numbering: u(cord1, θ, phi) appearing twice is one tap and one instruction."""
+    txt = _text("cfg2_bc").replace("u(cord1, θ, phi) .- 0.0", "(*).(u(cord1, θ, phi), u(cord1, θ, phi)) .- sin.(u(cord1, θ, phi))")
+    jl = lower_loss_function(parse(txt), ["u"])
+    assert jl.taps == [(0, 0, ())] and [i[0] for i in jl.prog].count("tap") == 1
+    assert [i[0] for i in jl.prog] == ["tap", "mul", "sin", "sub"]
