@@ -936,11 +936,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_loss_grad_kernel(const __gri
     if (tid >= 128 && tid < 128 + (int)((sizeof(DevNet) * PINN_MAX_NETS + 127) / 128))
       tc::prefetch_l1(reinterpret_cast<const char*>(&P.nets[0]) + (tid - 128) * 128);
     const int dim = tm.dim, n_taps = tm.n_taps, n_used = tm.n_used, weighted = tm.weighted;
-    for (int i = tid; i < dim * kTcPts; i += kTcThreads) {
-      int pp = i / dim, r = i - pp * dim;
-      long long gp = p0 + pp;
-      if (gp >= n_pts) gp = n_pts - 1;
-      ms.Xs[r * kTcPts + pp] = pts[gp * dim + r];
+    // Collocation tile: one point = dim contiguous scalars (the reference's d x N train-set layout), so a full 128-point
+    // tile is ONE contiguous block of dim x 512 bytes.  The TMA unit copies it into shared memory in a single bulk transfer
+    // (cp.async.bulk + mbarrier transaction count; staged in the scratch array, free between tiles) and 128 threads
+    // transpose it to [row][point].  Partial last tiles (clamped rows) and callers' buffers that are not 16-byte aligned
+    // take the per-element path.
+    const float* tile_src = pts + p0 * dim;
+    const bool bulk_tile = (p0 + kTcPts <= n_pts) && dim <= kTcMaxC && ((reinterpret_cast<uintptr_t>(tile_src) & 15) == 0);
+    if (bulk_tile) {
+      uint32_t ldp = (phase >> 1) & 1u;
+      if (tid == 0) {
+        tc::mbar_arrive_expect_tx(ms.bar_ld, (uint32_t)(dim * kTcPts * 4));
+        tc::bulk_load(ms.scratch, tile_src, (uint32_t)(dim * kTcPts * 4), ms.bar_ld);
+      }
+      wait_bar(ms.bar_ld, ldp);
+      phase = (phase & 1u) | (ldp << 1);
+      if (tid < kTcPts)
+        for (int r = 0; r < dim; ++r) ms.Xs[r * kTcPts + tid] = ms.scratch[tid * dim + r];
+    } else {
+      for (int i = tid; i < dim * kTcPts; i += kTcThreads) {
+        int pp = i / dim, r = i - pp * dim;
+        long long gp = p0 + pp;
+        if (gp >= n_pts) gp = n_pts - 1;
+        ms.Xs[r * kTcPts + pp] = pts[gp * dim + r];
+      }
     }
     if (tid < kTcPts) {
       long long gp = p0 + tid;
