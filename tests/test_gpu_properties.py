@@ -286,3 +286,36 @@ def test_third_order_ode_as_the_reference_states_it():
     pred = prob.representation.phi[0](xs.reshape(1, -1), res.x)[0]
     print("3rd-order ODE system: loss %.3e after %d BFGS iterations, max |u - analytic| %.2e" % (res.fun, res.nit, np.max(np.abs(pred - analytic))))
     np.testing.assert_allclose(pred, analytic, atol=1e-4)      # the reference's tolerance (:127)
+
+
+@pytest.mark.parametrize("kind", ["grid", "stochastic", "quasirandom"])
+def test_2d_poisson_as_the_reference_tests_it(kind):
+    """reference test/NNPDE1/nnpde__pde_ii_2d_poisson.jl:57-97: Chain(Dense(2,12,σ), Dense(12,12,σ), Dense(12,1)), the training
+    strategies of the test set-up (:20-35), Adam(0.01) for 1000 iterations, then `u_predict ≈ u_real atol = 2.0` on the
+    101 x 101 lattice against sin(pi x) sin(pi y) / (2 pi^2) (norm-wise).  Here the 1000 Adam iterations run in the
+    device-resident loop (samplers on the device for the sampling strategies); the reference's BFGS polish is not needed for
+    its tolerance.  A float64 PyTorch twin of this run lands at a norm error of 0.63-0.82; stated bound here 1.5."""
+    x, y = npde.parameters("x y")
+    u = npde.variables("u")
+    import sympy as sp
+    eq = npde.Eq((npde.Differential(x) ** 2)(u(x, y)) + (npde.Differential(y) ** 2)(u(x, y)), -sp.sin(sp.pi * x) * sp.sin(sp.pi * y))
+    bcs = [npde.Eq(u(0, y), 0.0), npde.Eq(u(1, y), 0.0), npde.Eq(u(x, 0), 0.0), npde.Eq(u(x, 1), 0.0)]
+    sys_ = npde.PDESystem(eq, bcs, [npde.In(x, 0.0, 1.0), npde.In(y, 0.0, 1.0)], [x, y], [u(x, y)])
+    chain = npde.Chain(npde.Dense(2, 12, "sigmoid"), npde.Dense(12, 12, "sigmoid"), npde.Dense(12, 1))
+    from neuralpde_jl_b200.strategies import QuasiRandomTraining
+    strategy = {"grid": npde.GridTraining(0.1),
+                "stochastic": npde.StochasticTraining(100, bcs_points=50, seed=1),
+                "quasirandom": QuasiRandomTraining(100, bcs_points=50, resampling=True, seed=1)}[kind]
+    if kind != "grid":
+        strategy.device_sampler = True
+    theta0 = npde.initialparameters(np.random.default_rng(0), chain, np.float64)
+    prob = npde.discretize(sys_, npde.PhysicsInformedNN(chain, strategy, init_params=theta0))
+    res = npde.solve(prob, npde.Adam(0.01), maxiters=1000, device_loop=True, chunk=250)
+    xs = np.arange(0.0, 1.0001, 0.01)
+    X, Y = np.meshgrid(xs, xs, indexing="ij")
+    pred = prob.representation.phi(np.stack([X.ravel(), Y.ravel()]), res.u)[0]
+    real = np.sin(np.pi * X.ravel()) * np.sin(np.pi * Y.ravel()) / (2 * np.pi ** 2)
+    err = float(np.linalg.norm(pred - real))
+    print("2-D Poisson (%s): loss %.3e, ||u_predict - u_real|| = %.3f over 10201 points" % (kind, res.objective, err))
+    assert err < 2.0          # the reference's tolerance (:97)
+    assert err < 1.5 and np.isfinite(res.objective)
