@@ -825,6 +825,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
   // ---- per-CTA setup --------------------------------------------------------------------------------------------------------
   if (tid == 0) {
     tc::mbar_init(ms.bar_mma, 1);
+    tc::mbar_init(ms.bar_ld, 1);            // collocation-tile bulk loads (own barrier: the weight stream uses cs.bar_ld[])
     for (int b = 0; b < 2; ++b) {
       tc::mbar_init(&cs.bar_ld[b], 1);
       tc::mbar_init(&cs.bar_free[b], 1);
@@ -901,6 +902,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
   __syncthreads();
   dbg_mark(&cs, 2);
   uint32_t phase = 0;
+  uint32_t tile_ld_phase = 0;      // parity of the collocation-tile barrier (ms.bar_ld)
 
   // tiles are claimed dynamically after the first one (heavy PDE tiles come first in the enumeration, cheap boundary
   // tiles last): a static round-robin leaves the CTAs that drew an extra PDE tile 20 % behind the rest
@@ -915,11 +917,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) tw_loss_grad_kernel(const __gri
     const float* qw = reinterpret_cast<const float*>(args.dyn[ti].qw);
     if (tid < (int)((sizeof(DevTerm) + 127) / 128)) tc::prefetch_l1(reinterpret_cast<const char*>(tmp) + tid * 128);
     const int dim = tm.dim, n_taps = tm.n_taps, n_used = tm.n_used, weighted = tm.weighted;
-    for (int i = tid; i < dim * kTcPts; i += kTcThreads) {
-      int pp = i / dim, r = i - pp * dim;
-      long long gp = p0 + pp;
-      if (gp >= n_pts) gp = n_pts - 1;
-      ms.Xs[r * kTcPts + pp] = pts[gp * dim + r];
+    // collocation tile = one contiguous block of dim x 512 bytes: one bulk transfer of the TMA unit into the scratch array,
+    // transposed to [row][point] by 128 threads (see tc_kernel.cu); partial / unaligned tiles take the per-element path
+    const float* tile_src = pts + p0 * dim;
+    const bool bulk_tile = (p0 + kTcPts <= n_pts) && dim <= kTwMaxC && ((reinterpret_cast<uintptr_t>(tile_src) & 15) == 0);
+    if (bulk_tile) {
+      if (tid == 0) {
+        tc::mbar_arrive_expect_tx(ms.bar_ld, (uint32_t)(dim * kTcPts * 4));
+        tc::bulk_load(ms.scratch, tile_src, (uint32_t)(dim * kTcPts * 4), ms.bar_ld);
+      }
+      wait_bar(ms.bar_ld, tile_ld_phase);
+      if (tid < kTcPts)
+        for (int r = 0; r < dim; ++r) ms.Xs[r * kTcPts + tid] = ms.scratch[tid * dim + r];
+    } else {
+      for (int i = tid; i < dim * kTcPts; i += kTcThreads) {
+        int pp = i / dim, r = i - pp * dim;
+        long long gp = p0 + pp;
+        if (gp >= n_pts) gp = n_pts - 1;
+        ms.Xs[r * kTcPts + pp] = pts[gp * dim + r];
+      }
     }
     if (tid < kTcPts) {
       long long gp = p0 + tid;
